@@ -1,0 +1,193 @@
+/*
+ * psam_b200.h -- C ABI of libpsam_b200.so: the ProtoSAM coarse-segmentation hot path
+ * (ALP prototype pooling, cosine matching, coarse-map -> SAM prompts) as sm_100a CUDA.
+ *
+ * The reference (levayz/ProtoSAM) is pure Python: it has no FFI, plugin table or
+ * operator registry for this path.  The "drop-in boundary" is the
+ * nn.Module / helper-function surface listed below; each entry point here names the
+ * reference interface it replaces (file:line relative to the reference tree) and is what
+ * a ctypes binding in the reference would call (INTEGRATION.md shows that stub).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless marked "host".
+ *     The library allocates nothing; scratch comes in through `workspace`.
+ *   - All work is enqueued on `stream` (a cudaStream_t); no entry point synchronises the
+ *     host.  Nothing is cached between calls; calls on different streams are independent.
+ *   - Return value: 0 = enqueued; negative = argument/launch error (see psam_last_error()).
+ *     Data-dependent conditions (empty prototype set, table overflow) are reported in
+ *     device-side status words so that no host sync is needed to launch the next stage.
+ *   - fp32 throughout; integer outputs are bit-exact w.r.t. the reference's CPU code,
+ *     maps are within 1e-3 absolute (BASELINE.json north_star).
+ */
+#ifndef PSAM_B200_H
+#define PSAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSAM_ABI_VERSION 1
+
+typedef void* psam_stream_t; /* cudaStream_t */
+
+/* Prototype modes of MultiProtoAsConv (models/alpmodule.py:57-94, 97-159). */
+#define PSAM_MODE_MASK          0 /* 'mask'      : one global masked-average prototype per shot  */
+#define PSAM_MODE_GRIDCONV      1 /* 'gridconv'  : local grid prototypes only                   */
+#define PSAM_MODE_GRIDCONV_PLUS 2 /* 'gridconv+' : local grid prototypes + the global prototype */
+/* Caller-side decision of FewShotSeg.forward (models/grid_proto_fewshot.py:250-256), taken on
+ * the device: 'gridconv+' if max(avg_pool2d(mask, auto_k)) >= thresh else 'mask'. */
+#define PSAM_MODE_AUTO_FG       3
+
+/* Bits of the per-set status word written by psam_alp_prototypes / psam_alp_match. */
+#define PSAM_SET_EMPTY 1 /* grid mode with zero prototypes: the reference raises inside F.conv2d
+                            (models/alpmodule.py:68); scores are NaN */
+
+/* Error codes. */
+#define PSAM_OK              0
+#define PSAM_ERR_ARG        -1
+#define PSAM_ERR_WORKSPACE  -2
+#define PSAM_ERR_LAUNCH     -3
+#define PSAM_ERR_UNSUPPORTED -4
+
+int psam_abi_version(void);
+/* Message of the last error on the calling thread ("" if none). */
+const char* psam_last_error(void);
+/* Number of kernels this library has launched on the calling process so far (bench.py's
+ * gpu_launches claim is read from here). */
+uint64_t psam_launch_count(void);
+
+/* --------------------------------------------------------------------------------------
+ * Kernel 1 -- prototypes.  Replaces MultiProtoAsConv.get_prototypes + safe_norm
+ * (models/alpmodule.py:14-18, 97-159) for `nsets` prototype sets that share one support
+ * feature tensor (e.g. background + foreground set of every label of a volume).
+ *
+ *   sup_x         [S,C,h,w] logical, addressed through `sup_x_strides` (host array of 4
+ *                 element strides: shot, channel, row, col) -- the reference hands over a
+ *                 physically channels-last tensor (stride_c == 1), which is the fast case.
+ *   sup_y         [nsets,S,h,w] contiguous masks (float, usually {0,1}).
+ *   set_modes     host [nsets] PSAM_MODE_*.
+ *   kh,kw         pooling window = stride (val_wsize when isval, else module kernel_size).
+ *   auto_kh/kw    window of the AUTO_FG decision (module kernel_size); ignored otherwise.
+ *   thresh        survivors are windows with mean(mask) > thresh (:131,153).
+ * Outputs (N = S*(h/kh)*(w/kw); cap_rows = N + S):
+ *   protos        [nsets,cap_rows,C] set i holds counts[i] L2-normalised rows (norm clamped
+ *                 at 1e-4): surviving windows in (shot,gy,gx) order, then S global rows for
+ *                 'gridconv+'; 'mask' sets hold their S global rows only.
+ *   counts        [nsets] int32 rows in use;  eff_modes [nsets] resolved mode (AUTO_FG).
+ *   status        [nsets] int32 PSAM_SET_* bits.
+ *   survive       [nsets,N] uint8 (bit-exact gate);  pooled [nsets,N] window mask fraction.
+ * ------------------------------------------------------------------------------------ */
+size_t psam_alp_prototypes_workspace(int nsets, int S, int C, int h, int w, int kh, int kw);
+
+int psam_alp_prototypes(const float* sup_x, const int64_t* sup_x_strides, const float* sup_y,
+                        int nsets, const int32_t* set_modes, int S, int C, int h, int w,
+                        int kh, int kw, int auto_kh, int auto_kw, float thresh,
+                        float* protos, int32_t* counts, int32_t* eff_modes, int32_t* status,
+                        uint8_t* survive, float* pooled,
+                        void* workspace, size_t workspace_bytes, psam_stream_t stream);
+
+/* Viz grid returned as 4th output of MultiProtoAsConv.forward for the grid modes
+ * (`resized_proto_grid`, models/alpmodule.py:120-128, 142-150) from the `pooled` values of one
+ * set: out [gh*vw, gw*vw] float32 (the reference builds it on the CPU in a Python loop). */
+int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, int vw, float thresh,
+                        int mode, float* out, psam_stream_t stream);
+
+/* --------------------------------------------------------------------------------------
+ * Kernel 2 -- fused match.  Replaces safe_norm(qry) + get_prediction_from_prototypes
+ * (models/alpmodule.py:57-94, 195) for Q query slices against all `nsets` sets at once.
+ *
+ *   qry        [Q,HW,C] channels-last rows: element (q,p,c) at qry[q*slice_stride + p*row_stride + c].
+ *   protos/counts/eff_modes   as written by psam_alp_prototypes (cap_rows rows per set).
+ *   scores     [Q,nsets,HW]  grid modes: sum_p softmax_p(d) * d with d = 20*cos;  mask: max_s d.
+ *              With sets ordered (bg_0, fg_0, bg_1, fg_1, ...) this buffer *is* the
+ *              [Q*L,2,h,w] logits tensor FewShotSeg concatenates (grid_proto_fewshot.py:270).
+ *   assign     [Q,nsets,HW] or NULL: argmax_p d as float (grid modes) / the score (mask mode).
+ *   sims       [Q,nsets,cap_rows,HW] or NULL: raw d ('raw_local_sims', vis_sim=True).
+ *   status     [nsets] int32, PSAM_SET_EMPTY is OR-ed in for empty grid sets.
+ *   algo       0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 split-bf16 tensor-core kernel.
+ * ------------------------------------------------------------------------------------ */
+size_t psam_alp_match_workspace(int Q, int HW, int C, int nsets, int cap_rows, int algo);
+
+int psam_alp_match(const float* qry, int64_t slice_stride, int64_t row_stride, int Q, int HW, int C,
+                   const float* protos, int cap_rows, const int32_t* counts, const int32_t* eff_modes,
+                   int nsets, float* scores, float* assign, float* sims, int32_t* status,
+                   void* workspace, size_t workspace_bytes, int algo, psam_stream_t stream);
+
+/* --------------------------------------------------------------------------------------
+ * Kernel 3 -- coarse map -> prompts.  Replaces, per image (= one query slice x one label):
+ *   F.interpolate(pred, img_size, 'bilinear')              models/grid_proto_fewshot.py:270-273
+ *   F.interpolate(logits, 1024, 'bilinear'), softmax, argmax    models/ProtoSAM.py:592-602
+ *   get_connected_components / cca                         util/utils.py:474-541
+ *   get_bbox_per_cc, get_most_conf_points, centroids       models/ProtoSAM.py:242-289, 349-450
+ * ------------------------------------------------------------------------------------ */
+
+/* One connected component, in OpenCV label order.  96 bytes. */
+typedef struct psam_prompt_rec {
+    int64_t box[4];      /* min_x, min_y, max_x, max_y (inclusive)   ProtoSAM.py:242-264      */
+    int64_t conf_pt[2];  /* x, y of torch.topk(p_fg[mask], 1)        ProtoSAM.py:266-289      */
+    double  centroid[2]; /* x, y = integer sums / area in double     cv2 centroids            */
+    double  conf;        /* sum(p_fg over component) / (n_fg + 1e-6) util/utils.py:490        */
+    float   conf_pt_p;   /* p_fg at conf_pt                                                   */
+    int32_t area;
+    int32_t label;       /* label cv2.connectedComponentsWithStats gives this component       */
+    int32_t flags;       /* PSAM_REC_* */
+    int32_t reserved[2];
+} psam_prompt_rec;
+
+#define PSAM_REC_SELECTED 1 /* the component `cca` keeps (use_cca) */
+
+/* Per-image header.  64 bytes. */
+typedef struct psam_image_hdr {
+    int32_t ncc;         /* foreground components found (cv2 count - 1)                        */
+    int32_t n_rec;       /* records written: min(ncc, max_cc), or 0/1 with use_cca             */
+    int32_t n_fg;        /* foreground pixels (= _pred.sum())                                  */
+    int32_t flags;       /* PSAM_IMG_*                                                         */
+    int32_t bg_stats[5]; /* cv2 stats row 0: left, top, width, height, area of the background  */
+    int32_t n_runs;      /* foreground runs found (diagnostic)                                 */
+    double  bg_centroid[2];
+    int32_t selected;    /* use_cca: cv2 label of the kept component, 0 if none                */
+    int32_t reserved;
+} psam_image_hdr;
+
+#define PSAM_IMG_EMPTY          1 /* no foreground pixel: ProtoSAM.forward returns early (:612-613) */
+#define PSAM_IMG_RUN_OVERFLOW   2 /* more runs than the workspace was sized for: nothing emitted     */
+#define PSAM_IMG_CC_TRUNCATED   4 /* ncc > max_cc: only the first max_cc labels were emitted         */
+#define PSAM_IMG_CCA_AMBIGUOUS  8 /* use_cca: two components' confidences are closer than fp32 sum
+                                     rounding; the exact-sum winner was kept                         */
+
+/* logits [n_img,2,h,w] -> two-stage bilinear (h,w)->(mid,mid)->(out,out) (single stage when
+ * mid == out), 2-way softmax, foreground bit.  ATen-CPU operation order, so bit-exact with
+ * the reference's CPU run.  Outputs, each optional (NULL to skip) except maskbits:
+ *   p_fg     [n_img,out,out] float  probability of class 1 (written at every pixel)
+ *   maskbits [n_img,out,out/32] uint32, bit (x&31) of word (y, x>>5) = argmax == 1
+ *   probs2   [n_img,2,out,out] float  full softmax (`output_p`), for function-level parity */
+int psam_upsample_softmax(const float* logits, int n_img, int h, int w, int mid, int out,
+                          float* p_fg, uint32_t* maskbits, float* probs2, psam_stream_t stream);
+
+/* max_runs: capacity of the per-CTA run table (foreground row segments per image). */
+size_t psam_prompts_workspace(int n_img, int out, int max_runs, int max_cc);
+
+/* maskbits + p_fg -> headers and records.  use_cca != 0 keeps only the most confident
+ * component (util/utils.py:496-541).  labels_out (optional) [n_img,out,out] int32 receives
+ * the cv2-numbered label image (0/1 image of the kept component with use_cca). */
+int psam_components(const uint32_t* maskbits, const float* p_fg, int n_img, int out,
+                    int use_cca, int max_cc, int max_runs,
+                    psam_image_hdr* hdr, psam_prompt_rec* recs, int32_t* labels_out,
+                    void* workspace, size_t workspace_bytes, psam_stream_t stream);
+
+/* Both stages for a batch of images: what the volume engine calls.  p_fg / maskbits live in
+ * the workspace. */
+size_t psam_coarse_to_prompts_workspace(int n_img, int out, int max_runs, int max_cc);
+
+int psam_coarse_to_prompts(const float* logits, int n_img, int h, int w, int mid, int out,
+                           int use_cca, int max_cc, int max_runs,
+                           psam_image_hdr* hdr, psam_prompt_rec* recs,
+                           void* workspace, size_t workspace_bytes, psam_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSAM_B200_H */

@@ -1,0 +1,79 @@
+"""ctypes binding of libpsam_b200.so (include/psam_b200.h).
+
+The library is the product: there is no Python/PyTorch fallback.  ``load()`` raises if the
+shared object has not been built (``python -c 'import __graft_entry__ as g; g.build()'`` or
+``make -C protosam_b200/csrc``) and every wrapper raises ``RuntimeError`` with the library's own
+message when a call is rejected.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpsam_b200.so")
+
+MODE_MASK, MODE_GRIDCONV, MODE_GRIDCONV_PLUS, MODE_AUTO_FG = 0, 1, 2, 3
+MODE_IDS = {"mask": MODE_MASK, "gridconv": MODE_GRIDCONV, "gridconv+": MODE_GRIDCONV_PLUS, "auto_fg": MODE_AUTO_FG}
+MODE_NAMES = {v: k for k, v in MODE_IDS.items()}
+
+SET_EMPTY = 1
+IMG_EMPTY, IMG_RUN_OVERFLOW, IMG_CC_TRUNCATED, IMG_CCA_AMBIGUOUS = 1, 2, 4, 8
+REC_SELECTED = 1
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_sz = ctypes.c_size_t
+c_f = ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/psam_b200.h one to one
+SIGNATURES = {
+    "psam_abi_version": (c_i, []),
+    "psam_last_error": (ctypes.c_char_p, []),
+    "psam_launch_count": (ctypes.c_uint64, []),
+    "psam_alp_prototypes_workspace": (c_sz, [c_i] * 7),
+    "psam_alp_prototypes": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
+                                  c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "psam_alp_proto_grid": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
+    "psam_alp_match_workspace": (c_sz, [c_i] * 6),
+    "psam_alp_match": (c_i, [c_p, c_i64, c_i64, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p,
+                             c_p, c_sz, c_i, c_p]),
+    "psam_upsample_softmax": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "psam_prompts_workspace": (c_sz, [c_i] * 4),
+    "psam_components": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "psam_coarse_to_prompts_workspace": (c_sz, [c_i] * 4),
+    "psam_coarse_to_prompts": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library or fail loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"protosam_b200: CUDA library not built ({LIB_PATH} missing). Build it with "
+            "`make -C protosam_b200/csrc` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.psam_abi_version() != 1:
+        raise RuntimeError("protosam_b200: ABI version mismatch between _lib.py and libpsam_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().psam_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().psam_launch_count())

@@ -1,0 +1,78 @@
+// Shared host/device helpers of libpsam_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/psam_b200.h"
+
+namespace psam {
+
+// ---- host-side error plumbing (thread-local message, see psam_last_error) ----
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PSAM_CHECK_ARG(cond, ...)                     \
+    do {                                              \
+        if (!(cond)) {                                \
+            psam::set_error(__VA_ARGS__);             \
+            return PSAM_ERR_ARG;                      \
+        }                                             \
+    } while (0)
+
+#define PSAM_CHECK_LAUNCH(what)                                                        \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) {                                                      \
+            psam::set_error("%s: %s", what, cudaGetErrorString(e__));                  \
+            return PSAM_ERR_LAUNCH;                                                    \
+        }                                                                              \
+        psam::count_launch();                                                          \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Carves aligned sub-buffers out of the caller's workspace.
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T>
+    T* take(size_t n)
+    {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    size_t used() const { return align_up(off, 256); }
+};
+
+// ---- device helpers ----
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_excl_scan_i(int v, int lane)
+{
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    return inc - v;
+}
+
+}  // namespace psam

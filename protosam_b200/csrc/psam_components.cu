@@ -1,0 +1,600 @@
+// Kernel 3b -- mask bits + p_fg -> connected components -> SAM prompt records (sm_100a).
+//
+// Replaces, per image (one query slice x one label), the CPU tail of ProtoSAM.forward:
+//   cv2.connectedComponentsWithStats(pred, connectivity=8)       util/utils.py:478
+//   per-component confidence and `cca` selection                 util/utils.py:485-541
+//   get_bbox_per_cc, get_most_conf_points, centroids             models/ProtoSAM.py:242-289, 349-450
+// The reference moves the 1024^2 maps to the host and makes O(ncc) full-image numpy passes;
+// here one persistent CTA per image works on the 128 KB bit mask:
+//   rows -> foreground runs (ballot/popc) -> lock-free union-find over RUNS (8-connectivity =
+//   runs of adjacent rows overlapping within one pixel) -> component order = OpenCV's label
+//   order (rank of the component's first 2x2 block in block-raster order, from a 32 KB bitmap
+//   + popcount prefix, no sort) -> exact integer statistics with atomics.
+// p_fg is read only under foreground runs.  Everything is integer arithmetic, so results do
+// not depend on scheduling: p_fg of a foreground pixel lies in [0.5,1], i.e. is a multiple of
+// 2^-24, and its sums are accumulated exactly in 64-bit integers.
+//
+// Roofline: latency/HBM bound, small: algorithmic bytes per image = out^2/8 (bits) + 4*n_fg
+// (p_fg under the mask) read + 96*ncc written.
+#include "psam_common.cuh"
+
+namespace psam {
+
+constexpr int CT = 1024;         // threads per CTA
+constexpr int MAX_OUT = 1024;    // image side supported by the static tables below
+constexpr int KEY_WORDS = (MAX_OUT / 2) * (MAX_OUT / 2) / 32;  // bitmap over 2x2 blocks
+
+struct Acc {
+    unsigned long long sumx, sumy, sump, best;
+    unsigned int area, minx, miny, maxx, maxy;
+    int root;
+};
+
+struct CompParams {
+    const uint32_t* maskbits;
+    const float* p_fg;
+    int n_img, out, use_cca, max_cc, max_runs;
+    psam_image_hdr* hdr;
+    psam_prompt_rec* recs;
+    int32_t* labels_out;
+    // per-CTA scratch (index = blockIdx.x)
+    uint16_t *run_s, *run_e, *run_y;
+    int32_t* parent;
+    uint32_t* minkey;
+    unsigned long long* sump;
+    int32_t* rank;
+    Acc* acc;
+};
+
+__device__ __forceinline__ int uf_find(volatile int32_t* parent, int x)
+{
+    int p = parent[x];
+    while (p != x) { x = p; p = parent[x]; }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b)
+{
+    volatile int32_t* vp = parent;
+    for (;;) {
+        a = uf_find(vp, a);
+        b = uf_find(vp, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }   // attach the larger root under the smaller
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// sum of the bit positions of the set bits of w
+__device__ __forceinline__ int bitpos_sum(uint32_t w)
+{
+    return __popc(w & 0xAAAAAAAAu) + 2 * __popc(w & 0xCCCCCCCCu) + 4 * __popc(w & 0xF0F0F0F0u) +
+           8 * __popc(w & 0xFF00FF00u) + 16 * __popc(w & 0xFFFF0000u);
+}
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int o)
+{
+    unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, o);
+    hi = __shfl_xor_sync(0xffffffffu, hi, o);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// torch.topk(v, 1) for n < 64: libstdc++ nth_element replayed (oracle: psamo_topk1_pos).
+struct TK { float v; int i; };
+__device__ __forceinline__ void tk_swap(TK& a, TK& b) { TK t = a; a = b; b = t; }
+
+__device__ int topk1_small(TK* q, int n)
+{
+    int first = 0, last = n;
+    int depth = 0;
+    for (int m = n; m > 1; m >>= 1) ++depth;
+    depth *= 2;
+    while (last - first > 3) {
+        if (depth == 0) {
+            for (int i = first + 1; i < last; ++i)
+                if (q[i].v > q[first].v) tk_swap(q[i], q[first]);
+            return q[0].i;
+        }
+        --depth;
+        const int mid = first + (last - first) / 2;
+        {   // __move_median_to_first(first, first+1, mid, last-1)
+            TK &r = q[first], &a = q[first + 1], &b = q[mid], &c = q[last - 1];
+            if (a.v > b.v) {
+                if (b.v > c.v) tk_swap(r, b);
+                else if (a.v > c.v) tk_swap(r, c);
+                else tk_swap(r, a);
+            } else if (a.v > c.v) tk_swap(r, a);
+            else if (b.v > c.v) tk_swap(r, c);
+            else tk_swap(r, b);
+        }
+        int f = first + 1, l = last;   // __unguarded_partition(first+1, last, pivot=first)
+        for (;;) {
+            while (q[f].v > q[first].v) ++f;
+            --l;
+            while (q[first].v > q[l].v) --l;
+            if (!(f < l)) break;
+            tk_swap(q[f], q[l]);
+            ++f;
+        }
+        if (f <= 0) first = f; else last = f;   // nth == position 0
+    }
+    // __insertion_sort(first, last)
+    for (int i = first + 1; i < last; ++i) {
+        TK val = q[i];
+        if (val.v > q[first].v) {
+            for (int k = i; k > first; --k) q[k] = q[k - 1];
+            q[first] = val;
+        } else {
+            int cur = i, next = i - 1;
+            while (val.v > q[next].v) { q[cur] = q[next]; cur = next; --next; }
+            q[cur] = val;
+        }
+    }
+    return q[0].i;
+}
+
+__global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
+{
+    __shared__ int s_rowstart[MAX_OUT + 1];
+    extern __shared__ uint32_t s_dyn[];          // 2 * KEY_WORDS words (64 KB, opt-in)
+    uint32_t* s_bitmap = s_dyn;
+    uint32_t* s_prefix = s_dyn + KEY_WORDS;
+    __shared__ int s_scan[32];
+    __shared__ unsigned long long s_red64[32];
+    __shared__ int s_misc[16];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int out = P.out, wpr = out >> 5, bw = (out + 1) >> 1;
+    const int key_words = (bw * bw + 31) >> 5;
+    const size_t so = (size_t)blockIdx.x * P.max_runs;
+    uint16_t* run_s = P.run_s + so;
+    uint16_t* run_e = P.run_e + so;
+    uint16_t* run_y = P.run_y + so;
+    int32_t* parent = P.parent + so;
+    uint32_t* minkey = P.minkey + so;
+    unsigned long long* sump = P.sump + so;
+    int32_t* rank = P.rank + so;
+    Acc* acc = P.acc + (size_t)blockIdx.x * P.max_cc;
+
+    for (int img = blockIdx.x; img < P.n_img; img += gridDim.x) {
+        const uint32_t* bits = P.maskbits + (size_t)img * out * wpr;
+        const float* pfg = P.p_fg + (size_t)img * out * out;
+        psam_image_hdr* hdr = P.hdr + img;
+        psam_prompt_rec* recs = P.recs + (size_t)img * P.max_cc;
+        int32_t* labels = P.labels_out ? P.labels_out + (size_t)img * out * out : nullptr;
+
+        // ---- S1: runs per row, foreground count, background box/sums --------------------
+        int npix = 0;
+        unsigned int bminx = 0xffffffffu, bminy = 0xffffffffu, bmaxx = 0, bmaxy = 0;
+        unsigned long long bsx = 0, bsy = 0;
+        int bany = 0;
+        if (tid <= MAX_OUT) s_rowstart[tid] = 0;
+        if (tid == 0) s_rowstart[MAX_OUT] = 0;
+        __syncthreads();
+        for (int y = wid; y < out; y += CT / 32) {
+            const uint32_t word = lane < wpr ? bits[(size_t)y * wpr + lane] : 0u;
+            uint32_t prev_msb = __shfl_up_sync(0xffffffffu, word >> 31, 1);
+            if (lane == 0) prev_msb = 0;
+            const uint32_t starts = word & ~((word << 1) | prev_msb);
+            const int tot = warp_sum_i(__popc(starts));
+            npix += __popc(word);
+            if (lane < wpr) {
+                const uint32_t inv = ~word;
+                if (inv) {
+                    bany = 1;
+                    const unsigned int x0 = lane * 32 + (__ffs(inv) - 1), x1 = lane * 32 + 31 - __clz(inv);
+                    bminx = min(bminx, x0); bmaxx = max(bmaxx, x1);
+                    bminy = min(bminy, (unsigned)y); bmaxy = max(bmaxy, (unsigned)y);
+                    const int c = __popc(inv);
+                    bsx += (unsigned long long)(lane * 32) * c + bitpos_sum(inv);
+                    bsy += (unsigned long long)y * c;
+                }
+            }
+            if (lane == 0) s_rowstart[y] = tot;
+        }
+        // block reductions of the S1 scalars
+        npix = warp_sum_i(npix);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bminx = min(bminx, __shfl_xor_sync(0xffffffffu, bminx, o));
+            bminy = min(bminy, __shfl_xor_sync(0xffffffffu, bminy, o));
+            bmaxx = max(bmaxx, __shfl_xor_sync(0xffffffffu, bmaxx, o));
+            bmaxy = max(bmaxy, __shfl_xor_sync(0xffffffffu, bmaxy, o));
+            bsx += shfl_xor_u64(bsx, o);
+            bsy += shfl_xor_u64(bsy, o);
+            bany |= __shfl_xor_sync(0xffffffffu, bany, o);
+        }
+        if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0x7fffffff; s_misc[2] = 0x7fffffff; s_misc[3] = 0; s_misc[4] = 0; s_misc[5] = 0; }
+        if (tid < 2) s_red64[tid] = 0;
+        __syncthreads();
+        if (lane == 0) {
+            atomicAdd(&s_misc[0], npix);
+            if (bany) {
+                atomicMin(&s_misc[1], (int)bminx); atomicMin(&s_misc[2], (int)bminy);
+                atomicMax(&s_misc[3], (int)bmaxx); atomicMax(&s_misc[4], (int)bmaxy);
+                atomicAdd(&s_red64[0], bsx); atomicAdd(&s_red64[1], bsy);
+                s_misc[5] = 1;
+            }
+        }
+        __syncthreads();
+        const int n_fg = s_misc[0];
+        const int n_bg = out * out - n_fg;
+
+        // ---- S2: exclusive scan of the per-row run counts --------------------------------
+        {
+            const int v = tid < out ? s_rowstart[tid] : 0;
+            const int ex = warp_excl_scan_i(v, lane);
+            if (lane == 31) s_scan[wid] = ex + v;
+            __syncthreads();
+            if (wid == 0) {
+                const int t = s_scan[lane];
+                const int e2 = warp_excl_scan_i(t, lane);
+                s_scan[lane] = e2;
+                if (lane == 31) s_misc[6] = e2 + t;
+            }
+            __syncthreads();
+            if (tid < out) s_rowstart[tid] = s_scan[wid] + ex;
+            if (tid == 0) s_rowstart[out] = s_misc[6];
+            __syncthreads();
+        }
+        const int total = s_rowstart[out];
+
+        if (tid == 0) {
+            hdr->n_fg = n_fg;
+            hdr->n_runs = total;
+            hdr->bg_stats[0] = s_misc[5] ? s_misc[1] : 0;
+            hdr->bg_stats[1] = s_misc[5] ? s_misc[2] : 0;
+            hdr->bg_stats[2] = s_misc[5] ? s_misc[3] - s_misc[1] + 1 : 0;
+            hdr->bg_stats[3] = s_misc[5] ? s_misc[4] - s_misc[2] + 1 : 0;
+            hdr->bg_stats[4] = n_bg;
+            hdr->bg_centroid[0] = n_bg ? (double)s_red64[0] / (double)n_bg : 0.0;
+            hdr->bg_centroid[1] = n_bg ? (double)s_red64[1] / (double)n_bg : 0.0;
+            hdr->selected = 0;
+            hdr->reserved = 0;
+        }
+        if (total == 0 || total > P.max_runs) {
+            if (tid == 0) {
+                hdr->ncc = 0;
+                hdr->n_rec = 0;
+                hdr->flags = total == 0 ? PSAM_IMG_EMPTY : PSAM_IMG_RUN_OVERFLOW;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- S3: materialise the runs -----------------------------------------------------
+        for (int y = wid; y < out; y += CT / 32) {
+            const uint32_t word = lane < wpr ? bits[(size_t)y * wpr + lane] : 0u;
+            uint32_t prev_msb = __shfl_up_sync(0xffffffffu, word >> 31, 1);
+            if (lane == 0) prev_msb = 0;
+            uint32_t next_lsb = __shfl_down_sync(0xffffffffu, word & 1u, 1);
+            if (lane == 31) next_lsb = 0;
+            uint32_t starts = word & ~((word << 1) | prev_msb);
+            uint32_t ends = word & ~((word >> 1) | (next_lsb << 31));
+            int si = s_rowstart[y] + warp_excl_scan_i(__popc(starts), lane);
+            int ei = s_rowstart[y] + warp_excl_scan_i(__popc(ends), lane);
+            while (starts) {
+                const int b = __ffs(starts) - 1;
+                starts &= starts - 1;
+                run_s[si] = (uint16_t)(lane * 32 + b);
+                run_y[si] = (uint16_t)y;
+                parent[si] = si;
+                minkey[si] = 0xffffffffu;
+                sump[si] = 0ull;
+                ++si;
+            }
+            while (ends) {
+                const int b = __ffs(ends) - 1;
+                ends &= ends - 1;
+                run_e[ei] = (uint16_t)(lane * 32 + b);
+                ++ei;
+            }
+        }
+        for (int i = tid; i < key_words; i += CT) s_bitmap[i] = 0u;
+        __syncthreads();
+
+        // ---- S4: union runs of adjacent rows that touch (8-connectivity) -------------------
+        for (int i = tid; i < total; i += CT) {
+            const int y = run_y[i];
+            if (y == 0) continue;
+            const int s = run_s[i], e = run_e[i];
+            int lo = s_rowstart[y - 1];
+            const int hi = s_rowstart[y];
+            int l = lo, r = hi;   // first j with run_e[j] >= s - 1
+            while (l < r) {
+                const int m = (l + r) >> 1;
+                if ((int)run_e[m] < s - 1) l = m + 1; else r = m;
+            }
+            for (int j = l; j < hi && (int)run_s[j] <= e + 1; ++j) uf_union(parent, i, j);
+        }
+        __syncthreads();
+        // ---- S5/S6: flatten; first 2x2 block (block-raster order) of every component -------
+        for (int i = tid; i < total; i += CT) {
+            const int r = uf_find(parent, i);
+            const uint32_t key = (uint32_t)(run_y[i] >> 1) * bw + (run_s[i] >> 1);
+            atomicMin(&minkey[r], key);
+            rank[i] = r;   // stash the root; parent[] stays a valid forest for concurrent finds
+        }
+        __syncthreads();
+        for (int i = tid; i < total; i += CT) parent[i] = rank[i];
+        __syncthreads();
+        // ---- S7-S9: OpenCV label = 1 + rank of that block among all components' first blocks
+        for (int i = tid; i < total; i += CT)
+            if (parent[i] == i) atomicOr(&s_bitmap[minkey[i] >> 5], 1u << (minkey[i] & 31));
+        __syncthreads();
+        {
+            const int per = (key_words + CT - 1) / CT;
+            const int w0 = tid * per;
+            int local = 0;
+            for (int k = 0; k < per; ++k)
+                if (w0 + k < key_words) local += __popc(s_bitmap[w0 + k]);
+            const int ex = warp_excl_scan_i(local, lane);
+            if (lane == 31) s_scan[wid] = ex + local;
+            __syncthreads();
+            if (wid == 0) {
+                const int t = s_scan[lane];
+                const int e2 = warp_excl_scan_i(t, lane);
+                s_scan[lane] = e2;
+                if (lane == 31) s_misc[7] = e2 + t;
+            }
+            __syncthreads();
+            int run = s_scan[wid] + ex;
+            for (int k = 0; k < per; ++k)
+                if (w0 + k < key_words) { s_prefix[w0 + k] = run; run += __popc(s_bitmap[w0 + k]); }
+            __syncthreads();
+        }
+        const int ncc = s_misc[7];
+        for (int i = tid; i < total; i += CT)
+            if (parent[i] == i) {
+                const uint32_t k = minkey[i];
+                rank[i] = (int)s_prefix[k >> 5] + __popc(s_bitmap[k >> 5] & ((1u << (k & 31)) - 1u));
+            }
+        __syncthreads();
+
+        // ---- S10: use_cca -- exact per-component sums of p_fg, keep the largest ------------
+        int sel_root = -1, flags = 0;
+        if (P.use_cca) {
+            for (int i = wid; i < total; i += CT / 32) {
+                const int y = run_y[i], s = run_s[i], e = run_e[i];
+                unsigned long long acc_p = 0;
+                for (int x = s + lane; x <= e; x += 32)
+                    acc_p += (unsigned long long)(pfg[(size_t)y * out + x] * 16777216.0f);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc_p += shfl_xor_u64(acc_p, o);
+                if (lane == 0) atomicAdd(&sump[parent[i]], acc_p);
+            }
+            __syncthreads();
+            // strictly largest confidence, first label on ties (util/utils.py:511-515)
+            unsigned long long best = 0;
+            for (int i = tid; i < total; i += CT)
+                if (parent[i] == i) {
+                    const unsigned long long k = (sump[i] << 20) | (unsigned long long)(0xFFFFF - rank[i]);
+                    best = max(best, k);
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = max(best, shfl_xor_u64(best, o));
+            if (lane == 0) s_red64[wid] = best;
+            __syncthreads();
+            best = 0;
+            for (int k = 0; k < CT / 32; ++k) best = max(best, s_red64[k]);
+            __syncthreads();
+            const int best_rank = 0xFFFFF - (int)(best & 0xFFFFF);
+            const unsigned long long best_sum = best >> 20;
+            unsigned long long second = 0;
+            for (int i = tid; i < total; i += CT)
+                if (parent[i] == i) {
+                    if (rank[i] == best_rank) s_misc[8] = i;
+                    else second = max(second, sump[i]);
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) second = max(second, shfl_xor_u64(second, o));
+            if (lane == 0) s_red64[wid] = second;
+            __syncthreads();
+            second = 0;
+            for (int k = 0; k < CT / 32; ++k) second = max(second, s_red64[k]);
+            sel_root = s_misc[8];
+            // the reference compares fp32 pairwise sums (relative error < 4e-6): flag near-ties
+            if ((double)second * (1.0 + 1e-5) >= (double)best_sum) flags |= PSAM_IMG_CCA_AMBIGUOUS;
+            __syncthreads();
+        }
+
+        // ---- S11: statistics of the emitted components -------------------------------------
+        const int n_rec = P.use_cca ? 1 : min(ncc, P.max_cc);
+        if (!P.use_cca && ncc > P.max_cc) flags |= PSAM_IMG_CC_TRUNCATED;
+        for (int r = tid; r < n_rec; r += CT) {
+            Acc a;
+            a.sumx = 0; a.sumy = 0; a.sump = 0; a.best = 0;
+            a.area = 0; a.minx = 0xffffffffu; a.miny = 0xffffffffu; a.maxx = 0; a.maxy = 0; a.root = -1;
+            acc[r] = a;
+        }
+        __syncthreads();
+        for (int i = wid; i < total; i += CT / 32) {
+            const int root = parent[i];
+            const int slot = P.use_cca ? (root == sel_root ? 0 : -1) : (rank[root] < P.max_cc ? rank[root] : -1);
+            if (slot < 0) continue;
+            const int y = run_y[i], s = run_s[i], e = run_e[i];
+            unsigned long long acc_p = 0, best = 0;
+            for (int x = s + lane; x <= e; x += 32) {
+                const float pv = pfg[(size_t)y * out + x];
+                acc_p += (unsigned long long)(pv * 16777216.0f);
+                const unsigned long long k = ((unsigned long long)__float_as_uint(pv) << 32) |
+                                             (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * out + x));
+                best = max(best, k);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc_p += shfl_xor_u64(acc_p, o);
+                best = max(best, shfl_xor_u64(best, o));
+            }
+            if (lane == 0) {
+                Acc* a = acc + slot;
+                const unsigned int len = e - s + 1;
+                atomicAdd(&a->area, len);
+                atomicAdd(&a->sumx, (unsigned long long)(s + e) * len / 2);
+                atomicAdd(&a->sumy, (unsigned long long)y * len);
+                atomicAdd(&a->sump, acc_p);
+                atomicMax(&a->best, best);
+                atomicMin(&a->minx, (unsigned)s); atomicMax(&a->maxx, (unsigned)e);
+                atomicMin(&a->miny, (unsigned)y); atomicMax(&a->maxy, (unsigned)y);
+                if (i == root) a->root = root;
+            }
+        }
+        __syncthreads();
+
+        // ---- S12/S13: records (label order); small components replay torch.topk's nth_element
+        for (int r = tid; r < n_rec; r += CT) {
+            const Acc a = acc[r];
+            psam_prompt_rec rec;
+            rec.box[0] = a.minx; rec.box[1] = a.miny; rec.box[2] = a.maxx; rec.box[3] = a.maxy;
+            unsigned int idx = 0xFFFFFFFFu - (unsigned int)(a.best & 0xFFFFFFFFu);
+            float pbest = __uint_as_float((unsigned int)(a.best >> 32));
+            if (a.area < 64) {
+                TK q[64];
+                int n = 0;
+                for (unsigned int y = a.miny; y <= a.maxy; ++y)
+                    for (int j = s_rowstart[y]; j < s_rowstart[y + 1]; ++j)
+                        if (parent[j] == a.root)
+                            for (int x = run_s[j]; x <= (int)run_e[j]; ++x) {
+                                q[n].v = pfg[(size_t)y * out + x];
+                                q[n].i = (int)(y * out + x);
+                                ++n;
+                            }
+                idx = (unsigned int)topk1_small(q, n);
+                pbest = pfg[idx];
+            }
+            rec.conf_pt[0] = idx % out;
+            rec.conf_pt[1] = idx / out;
+            rec.centroid[0] = (double)a.sumx / (double)a.area;
+            rec.centroid[1] = (double)a.sumy / (double)a.area;
+            rec.conf = ((double)a.sump * (1.0 / 16777216.0)) / ((double)n_fg + 1e-6);
+            rec.conf_pt_p = pbest;
+            rec.area = (int)a.area;
+            rec.label = rank[a.root] + 1;
+            rec.flags = P.use_cca ? PSAM_REC_SELECTED : 0;
+            recs[r] = rec;
+            if (P.use_cca) hdr->selected = rec.label;
+        }
+        if (tid == 0) {
+            hdr->ncc = ncc;
+            hdr->n_rec = n_rec;
+            hdr->flags = flags;
+        }
+        // ---- optional label image (function-level API: cv2-style tuple) ---------------------
+        if (labels) {
+            for (int i = wid; i < total; i += CT / 32) {
+                const int root = parent[i];
+                const int lab = P.use_cca ? (root == sel_root ? 1 : 0) : rank[root] + 1;
+                const int y = run_y[i], s = run_s[i], e = run_e[i];
+                for (int x = s + lane; x <= e; x += 32) labels[(size_t)y * out + x] = lab;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace psam
+
+using namespace psam;
+
+static int comp_grid(int n_img)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return n_img < sms ? n_img : sms;
+}
+
+static size_t comp_scratch_bytes(int ctas, int max_runs, int max_cc)
+{
+    // arrays are carved per kind (all CTAs contiguous), see psam_components
+    size_t b = 0;
+    b += align_up(sizeof(uint16_t) * (size_t)ctas * max_runs, 256) * 3;
+    b += align_up(sizeof(int32_t) * (size_t)ctas * max_runs, 256) * 2;
+    b += align_up(sizeof(uint32_t) * (size_t)ctas * max_runs, 256);
+    b += align_up(sizeof(unsigned long long) * (size_t)ctas * max_runs, 256);
+    b += align_up(sizeof(Acc) * (size_t)ctas * max_cc, 256);
+    return b + 256;
+}
+
+extern "C" size_t psam_prompts_workspace(int n_img, int out, int max_runs, int max_cc)
+{
+    (void)out;
+    if (n_img <= 0 || max_runs <= 0 || max_cc <= 0) return 0;
+    return comp_scratch_bytes(comp_grid(n_img), max_runs, max_cc);
+}
+
+extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, int n_img, int out, int use_cca,
+                               int max_cc, int max_runs, psam_image_hdr* hdr, psam_prompt_rec* recs,
+                               int32_t* labels_out, void* workspace, size_t workspace_bytes, psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(maskbits && p_fg && hdr && recs && workspace, "psam_components: null pointer");
+    PSAM_CHECK_ARG(n_img >= 1, "psam_components: n_img %d", n_img);
+    PSAM_CHECK_ARG(out >= 32 && out <= MAX_OUT && out % 32 == 0, "psam_components: out=%d must be a multiple of 32 in [32,%d]", out, MAX_OUT);
+    PSAM_CHECK_ARG(max_cc >= 1 && max_cc <= (1 << 18), "psam_components: max_cc %d", max_cc);
+    PSAM_CHECK_ARG(max_runs >= 1 && max_runs <= (1 << 24), "psam_components: max_runs %d", max_runs);
+    const int ctas = comp_grid(n_img);
+    if (workspace_bytes < comp_scratch_bytes(ctas, max_runs, max_cc)) {
+        set_error("psam_components: workspace too small (%zu < %zu)", workspace_bytes, comp_scratch_bytes(ctas, max_runs, max_cc));
+        return PSAM_ERR_WORKSPACE;
+    }
+    CompParams P;
+    P.maskbits = maskbits; P.p_fg = p_fg; P.n_img = n_img; P.out = out; P.use_cca = use_cca ? 1 : 0;
+    P.max_cc = max_cc; P.max_runs = max_runs; P.hdr = hdr; P.recs = recs; P.labels_out = labels_out;
+    Carver cv(workspace);
+    const size_t n = (size_t)ctas * max_runs;
+    P.run_s = cv.take<uint16_t>(n);
+    P.run_e = cv.take<uint16_t>(n);
+    P.run_y = cv.take<uint16_t>(n);
+    P.parent = cv.take<int32_t>(n);
+    P.rank = cv.take<int32_t>(n);
+    P.minkey = cv.take<uint32_t>(n);
+    P.sump = cv.take<unsigned long long>(n);
+    P.acc = cv.take<Acc>((size_t)ctas * max_cc);
+    if (labels_out) {
+        cudaError_t e = cudaMemsetAsync(labels_out, 0, sizeof(int32_t) * (size_t)n_img * out * out, stream);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return PSAM_ERR_LAUNCH; }
+    }
+    const int dyn = 2 * KEY_WORDS * (int)sizeof(uint32_t);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PSAM_ERR_LAUNCH; }
+        attr_done = true;
+    }
+    k_components<<<ctas, CT, dyn, stream>>>(P);
+    PSAM_CHECK_LAUNCH("k_components");
+    return PSAM_OK;
+}
+
+extern "C" size_t psam_coarse_to_prompts_workspace(int n_img, int out, int max_runs, int max_cc)
+{
+    if (n_img <= 0 || out <= 0) return 0;
+    size_t b = 0;
+    b += align_up(sizeof(float) * (size_t)n_img * out * out, 256);            // p_fg
+    b += align_up(sizeof(uint32_t) * (size_t)n_img * out * (out / 32), 256);  // mask bits
+    b += psam_prompts_workspace(n_img, out, max_runs, max_cc);
+    return b + 256;
+}
+
+extern "C" int psam_coarse_to_prompts(const float* logits, int n_img, int h, int w, int mid, int out, int use_cca,
+                                      int max_cc, int max_runs, psam_image_hdr* hdr, psam_prompt_rec* recs,
+                                      void* workspace, size_t workspace_bytes, psam_stream_t stream)
+{
+    PSAM_CHECK_ARG(workspace, "psam_coarse_to_prompts: null workspace");
+    if (workspace_bytes < psam_coarse_to_prompts_workspace(n_img, out, max_runs, max_cc)) {
+        set_error("psam_coarse_to_prompts: workspace too small");
+        return PSAM_ERR_WORKSPACE;
+    }
+    Carver cv(workspace);
+    float* p_fg = cv.take<float>((size_t)n_img * out * out);
+    uint32_t* bits = cv.take<uint32_t>((size_t)n_img * out * (out / 32));
+    char* rest = static_cast<char*>(workspace) + cv.used();
+    int rc = psam_upsample_softmax(logits, n_img, h, w, mid, out, p_fg, bits, nullptr, stream);
+    if (rc) return rc;
+    return psam_components(bits, p_fg, n_img, out, use_cca, max_cc, max_runs, hdr, recs, nullptr, rest,
+                           workspace_bytes - cv.used(), stream);
+}

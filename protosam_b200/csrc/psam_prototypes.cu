@@ -1,0 +1,388 @@
+// Kernel 1 -- ALP prototype pass (sm_100a).
+//
+// Replaces MultiProtoAsConv.get_prototypes + safe_norm of the reference
+// (models/alpmodule.py:14-18, 97-159): masked grid average pooling, the foreground-fraction
+// threshold, ORDERED compaction of the surviving local prototypes ((shot,gy,gx) row-major,
+// which feeds debug_assign / proto_grid numbering), the global masked-average prototype and
+// the L2 normalisation, for many prototype sets that share one support feature tensor.
+//
+// Roofline: HBM-bound and tiny -- one read of the S*h*w*C support features per set
+// (4.2 MB at ViT-B/14 37x37) once per VOLUME, against Q reads of the same size in kernel 2.
+// Algorithmic bytes per set: 4*S*h*w*(C+1) read + 4*P*C written.  What matters here is
+// (a) no host synchronisation (the reference syncs four times: nonzero x2, boolean index,
+// .max() >= thresh) and (b) coalesced channels-last reads.
+#include "psam_common.cuh"
+
+namespace psam {
+
+constexpr int kMaxSets = 128;
+struct SetModes {
+    int8_t m[kMaxSets];
+};
+
+// ------------------------------------------------------------------------------------
+// K1a: per set -- window mask fractions (exact ATen order: sequential (dy,dx) sum, true
+// division), AUTO_FG decision, survive flags, ordered row indices, per-shot mask sums.
+// grid = nsets, block = 256.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pool_mask(const float* __restrict__ sup_y, SetModes modes, int S, int h,
+                                                   int w, int kh, int kw, int akh, int akw, float thresh,
+                                                   float* __restrict__ pooled, uint8_t* __restrict__ survive,
+                                                   int32_t* __restrict__ rowidx, float* __restrict__ ysum,
+                                                   int32_t* __restrict__ counts, int32_t* __restrict__ eff_modes,
+                                                   int32_t* __restrict__ status, int32_t* __restrict__ plocal)
+{
+    const int set = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gh = h / kh, gw = w / kw, N = S * gh * gw;
+    const float* y = sup_y + (size_t)set * S * h * w;
+    __shared__ int s_warp[8];
+    __shared__ int s_flag;
+    __shared__ float s_wsum[8];
+
+    int mode = modes.m[set];
+    if (mode == PSAM_MODE_AUTO_FG) {
+        // F.avg_pool2d(mask, kernel_size).max() >= thresh   (grid_proto_fewshot.py:254-256)
+        const int agh = h / akh, agw = w / akw, AN = S * agh * agw;
+        const float adiv = (float)(akh * akw);
+        int hit = 0;
+        for (int n = tid; n < AN; n += 256) {
+            int s = n / (agh * agw), r = n % (agh * agw), gy = r / agw, gx = r % agw;
+            const float* p = y + ((size_t)s * h + gy * akh) * w + gx * akw;
+            float acc = 0.0f;
+            for (int dy = 0; dy < akh; ++dy)
+                for (int dx = 0; dx < akw; ++dx) acc = __fadd_rn(acc, p[dy * w + dx]);
+            hit |= (__fdiv_rn(acc, adiv) >= thresh);
+        }
+        hit = __syncthreads_or(hit);
+        mode = hit ? PSAM_MODE_GRIDCONV_PLUS : PSAM_MODE_MASK;
+    }
+    const bool locals = (mode != PSAM_MODE_MASK);
+    const bool globals = (mode != PSAM_MODE_GRIDCONV);
+
+    // pooled fraction + survive + ordered compaction index
+    const float div = (float)(kh * kw);
+    int running = 0;
+    for (int base = 0; base < N; base += 256) {
+        int n = base + tid, flag = 0;
+        if (n < N) {
+            int s = n / (gh * gw), r = n % (gh * gw), gy = r / gw, gx = r % gw;
+            const float* p = y + ((size_t)s * h + gy * kh) * w + gx * kw;
+            float acc = 0.0f;
+            for (int dy = 0; dy < kh; ++dy)
+                for (int dx = 0; dx < kw; ++dx) acc = __fadd_rn(acc, p[dy * w + dx]);
+            float f = __fdiv_rn(acc, div);
+            pooled[(size_t)set * N + n] = f;
+            flag = locals && (f > thresh);
+            survive[(size_t)set * N + n] = (uint8_t)(f > thresh);
+        }
+        int ex = warp_excl_scan_i(flag, lane);
+        if (lane == 31) s_warp[wid] = ex + flag;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int v = s_warp[k];
+            if (k < wid) woff += v;
+            tot += v;
+        }
+        if (n < N) rowidx[(size_t)set * N + n] = flag ? running + woff + ex : -1;
+        running += tot;
+        __syncthreads();
+    }
+
+    // per-shot mask sums (denominator of the global prototype, alpmodule.py:100,156)
+    for (int s = 0; s < S; ++s) {
+        float acc = 0.0f;
+        for (int i = tid; i < h * w; i += 256) acc += y[(size_t)s * h * w + i];
+        acc = warp_sum(acc);
+        if (lane == 0) s_wsum[wid] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.0f;
+            for (int k = 0; k < 8; ++k) t += s_wsum[k];
+            ysum[set * S + s] = t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        plocal[set] = running;
+        counts[set] = running + (globals ? S : 0);
+        eff_modes[set] = mode;
+        status[set] = (mode == PSAM_MODE_GRIDCONV && running == 0) ? PSAM_SET_EMPTY : 0;
+    }
+    (void)s_flag;
+}
+
+// ------------------------------------------------------------------------------------
+// K1b: one CTA per (window, set): pooled feature vector of a surviving window, L2-normalised
+// (clamp 1e-4), written at its compacted row.  Threads run along C (coalesced when the
+// tensor is channels-last).  grid = (N, nsets), block = 256, C <= 256*16.
+// ------------------------------------------------------------------------------------
+constexpr int kMaxCPerThread = 16;
+
+__device__ __forceinline__ float block_sum_256(float v, float* s_red)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_red[k];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_pool_feat(const float* __restrict__ sup_x, int64_t xs_s, int64_t xs_c,
+                                                   int64_t xs_y, int64_t xs_x, const int32_t* __restrict__ rowidx,
+                                                   int S, int C, int h, int w, int kh, int kw, int cap_rows,
+                                                   float* __restrict__ protos)
+{
+    const int n = blockIdx.x, set = blockIdx.y, tid = threadIdx.x;
+    const int gh = h / kh, gw = w / kw, N = S * gh * gw;
+    const int row = rowidx[(size_t)set * N + n];
+    if (row < 0) return;
+    __shared__ float s_red[8];
+    const int s = n / (gh * gw), r = n % (gh * gw), gy = r / gw, gx = r % gw;
+    const float* base = sup_x + s * xs_s + (int64_t)(gy * kh) * xs_y + (int64_t)(gx * kw) * xs_x;
+    const float div = (float)(kh * kw);
+    float v[kMaxCPerThread];
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kMaxCPerThread; ++j) {
+        int c = tid + j * 256;
+        v[j] = 0.0f;
+        if (c < C) {
+            float acc = 0.0f;
+            for (int dy = 0; dy < kh; ++dy)
+                for (int dx = 0; dx < kw; ++dx) acc = __fadd_rn(acc, __ldg(base + c * xs_c + dy * xs_y + dx * xs_x));
+            v[j] = __fdiv_rn(acc, div);
+            ss += v[j] * v[j];
+        }
+    }
+    ss = block_sum_256(ss, s_red);
+    float nrm = fmaxf(sqrtf(ss), 1e-4f);
+    float* dst = protos + ((size_t)set * cap_rows + row) * C;
+#pragma unroll
+    for (int j = 0; j < kMaxCPerThread; ++j) {
+        int c = tid + j * 256;
+        if (c < C) dst[c] = v[j] / nrm;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K1c/K1d: global masked-average prototype  sum(x*y) / (sum(y) + 1e-5)  (alpmodule.py:99-100,
+// 155-156), deterministic two-stage reduction: partial sums per feature row, then a fixed
+// order combine + safe_norm.  grid K1c = (h, S, nsets); grid K1d = (S, nsets).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_global_partial(const float* __restrict__ sup_x, int64_t xs_s, int64_t xs_c,
+                                                        int64_t xs_y, int64_t xs_x, const float* __restrict__ sup_y,
+                                                        const int32_t* __restrict__ eff_modes, int S, int C, int h,
+                                                        int w, float* __restrict__ partial)
+{
+    const int yy = blockIdx.x, s = blockIdx.y, set = blockIdx.z, tid = threadIdx.x;
+    if (eff_modes[set] == PSAM_MODE_GRIDCONV) return;
+    const float* m = sup_y + (((size_t)set * S + s) * h + yy) * w;
+    const float* base = sup_x + s * xs_s + (int64_t)yy * xs_y;
+    float* dst = partial + (((size_t)set * S + s) * h + yy) * C;
+    for (int c = tid; c < C; c += 256) {
+        float acc = 0.0f;
+        for (int xx = 0; xx < w; ++xx) {
+            float mv = m[xx];
+            if (mv != 0.0f) acc += __ldg(base + c * xs_c + xx * xs_x) * mv;
+        }
+        dst[c] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_global_final(const float* __restrict__ partial,
+                                                      const float* __restrict__ ysum,
+                                                      const int32_t* __restrict__ eff_modes,
+                                                      const int32_t* __restrict__ plocal, int S, int C, int h,
+                                                      int cap_rows, float* __restrict__ protos)
+{
+    const int s = blockIdx.x, set = blockIdx.y, tid = threadIdx.x;
+    if (eff_modes[set] == PSAM_MODE_GRIDCONV) return;
+    __shared__ float s_red[8];
+    const float* src = partial + ((size_t)set * S + s) * h * C;
+    const float den = ysum[set * S + s] + 1e-5f;
+    float v[kMaxCPerThread];
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kMaxCPerThread; ++j) {
+        int c = tid + j * 256;
+        v[j] = 0.0f;
+        if (c < C) {
+            float acc = 0.0f;
+            for (int yy = 0; yy < h; ++yy) acc += src[(size_t)yy * C + c];
+            v[j] = acc / den;
+            ss += v[j] * v[j];
+        }
+    }
+    ss = block_sum_256(ss, s_red);
+    // safe_norm for the grid modes (:158); cosine_similarity's clamp_min(eps=1e-4) for 'mask'
+    // (:59) -- the same arithmetic.
+    float nrm = fmaxf(sqrtf(ss), 1e-4f);
+    float* dst = protos + ((size_t)set * cap_rows + plocal[set] + s) * C;
+#pragma unroll
+    for (int j = 0; j < kMaxCPerThread; ++j) {
+        int c = tid + j * 256;
+        if (c < C) dst[c] = v[j] / nrm;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Viz grid (`resized_proto_grid`, alpmodule.py:120-128 / 142-150).  One CTA.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_proto_grid(const float* __restrict__ pooled, int S, int gh, int gw, int vw,
+                                                    float thresh, int mode, float* __restrict__ out,
+                                                    int32_t* __restrict__ ord /* [S*gh*gw] scratch in out tail? */)
+{
+    // ord[n] = ordinal of entry n among the non-zero entries of the thresholded grid, or -1
+    extern __shared__ int32_t s_ord[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = S * gh * gw;
+    __shared__ int s_warp[8];
+    int running = 0;
+    for (int base = 0; base < N; base += 256) {
+        int n = base + tid, flag = 0;
+        if (n < N) {
+            float v = pooled[n];
+            flag = (!(v < thresh)) && (v != 0.0f);
+        }
+        int ex = warp_excl_scan_i(flag, lane);
+        if (lane == 31) s_warp[wid] = ex + flag;
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int v = s_warp[k];
+            if (k < wid) woff += v;
+            tot += v;
+        }
+        if (n < N) s_ord[n] = flag ? running + woff + ex : -1;
+        running += tot;
+        __syncthreads();
+    }
+    const int OH = gh * vw, OW = gw * vw;
+    for (int i = tid; i < OH * OW; i += 256) {
+        int Y = i / OW, X = i % OW, gy = Y / vw;
+        // candidate cells whose 2-wide stripe covers column X
+        int best_s = -1, best_gx = -1;
+        for (int cand = 0; cand < 2; ++cand) {
+            int gx;
+            if (cand == 0) {
+                gx = X / vw;
+                if (X - gx * vw >= 2) continue;
+            } else {
+                if (vw != 1 || X == 0) continue;
+                gx = X - 1;
+            }
+            for (int s = S - 1; s >= 0; --s)
+                if (s_ord[(s * gh + gy) * gw + gx] >= 0) {
+                    if (s > best_s || (s == best_s && gx > best_gx)) { best_s = s; best_gx = gx; }
+                    break;
+                }
+        }
+        float val = 0.0f;
+        if (best_s >= 0) {
+            int cell = gy * gw + best_gx;   // value always read from shot 0's plane (:128,150)
+            if (mode == PSAM_MODE_GRIDCONV_PLUS) {
+                int last = -1;              // renumbering (:146-147): last non-zero entry at this cell wins
+                for (int s = S - 1; s >= 0 && last < 0; --s) last = s_ord[s * gh * gw + cell];
+                val = (float)(last + 1);
+            } else {
+                float v0 = pooled[cell];
+                val = (s_ord[cell] >= 0) ? v0 : 0.0f;
+            }
+        }
+        out[i] = val;
+    }
+    (void)ord;
+}
+
+}  // namespace psam
+
+using namespace psam;
+
+extern "C" size_t psam_alp_prototypes_workspace(int nsets, int S, int C, int h, int w, int kh, int kw)
+{
+    if (nsets <= 0 || S <= 0 || C <= 0 || h <= 0 || w <= 0 || kh <= 0 || kw <= 0) return 0;
+    size_t N = (size_t)S * (h / kh) * (w / kw);
+    size_t b = 0;
+    b += align_up(sizeof(int32_t) * nsets * (N ? N : 1), 256);      // rowidx
+    b += align_up(sizeof(float) * nsets * S, 256);                  // ysum
+    b += align_up(sizeof(int32_t) * nsets, 256);                    // plocal
+    b += align_up(sizeof(float) * (size_t)nsets * S * h * C, 256);  // partial
+    return b + 256;
+}
+
+extern "C" int psam_alp_prototypes(const float* sup_x, const int64_t* xs, const float* sup_y, int nsets,
+                                   const int32_t* set_modes, int S, int C, int h, int w, int kh, int kw,
+                                   int auto_kh, int auto_kw, float thresh, float* protos, int32_t* counts,
+                                   int32_t* eff_modes, int32_t* status, uint8_t* survive, float* pooled,
+                                   void* workspace, size_t workspace_bytes, psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(sup_x && xs && sup_y && set_modes && protos && counts && eff_modes && status && survive && pooled,
+                   "psam_alp_prototypes: null pointer");
+    PSAM_CHECK_ARG(nsets >= 1 && nsets <= kMaxSets, "psam_alp_prototypes: nsets %d not in [1,%d]", nsets, kMaxSets);
+    PSAM_CHECK_ARG(S >= 1 && C >= 1 && h >= 1 && w >= 1, "psam_alp_prototypes: bad shape");
+    PSAM_CHECK_ARG(C <= 256 * kMaxCPerThread, "psam_alp_prototypes: C=%d exceeds %d", C, 256 * kMaxCPerThread);
+    PSAM_CHECK_ARG(kh >= 1 && kw >= 1 && kh <= h && kw <= w, "psam_alp_prototypes: window %dx%d vs map %dx%d", kh, kw, h, w);
+    SetModes modes;
+    bool any_auto = false;
+    for (int i = 0; i < nsets; ++i) {
+        PSAM_CHECK_ARG(set_modes[i] >= 0 && set_modes[i] <= 3, "psam_alp_prototypes: invalid mode %d", set_modes[i]);
+        modes.m[i] = (int8_t)set_modes[i];
+        any_auto |= set_modes[i] == PSAM_MODE_AUTO_FG;
+    }
+    if (any_auto)
+        PSAM_CHECK_ARG(auto_kh >= 1 && auto_kw >= 1 && auto_kh <= h && auto_kw <= w,
+                       "psam_alp_prototypes: AUTO_FG needs a valid auto window");
+    else
+        auto_kh = auto_kw = 1;
+    if (workspace_bytes < psam_alp_prototypes_workspace(nsets, S, C, h, w, kh, kw) || !workspace) {
+        set_error("psam_alp_prototypes: workspace too small");
+        return PSAM_ERR_WORKSPACE;
+    }
+    const int gh = h / kh, gw = w / kw, N = S * gh * gw, cap_rows = N + S;
+    Carver cv(workspace);
+    int32_t* rowidx = cv.take<int32_t>((size_t)nsets * (N ? N : 1));
+    float* ysum = cv.take<float>((size_t)nsets * S);
+    int32_t* plocal = cv.take<int32_t>(nsets);
+    float* partial = cv.take<float>((size_t)nsets * S * h * C);
+
+    k_pool_mask<<<nsets, 256, 0, stream>>>(sup_y, modes, S, h, w, kh, kw, auto_kh, auto_kw, thresh, pooled, survive,
+                                           rowidx, ysum, counts, eff_modes, status, plocal);
+    PSAM_CHECK_LAUNCH("k_pool_mask");
+    if (N > 0) {
+        k_pool_feat<<<dim3(N, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], rowidx, S, C, h, w, kh, kw,
+                                                        cap_rows, protos);
+        PSAM_CHECK_LAUNCH("k_pool_feat");
+    }
+    k_global_partial<<<dim3(h, S, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], sup_y, eff_modes, S, C,
+                                                            h, w, partial);
+    PSAM_CHECK_LAUNCH("k_global_partial");
+    k_global_final<<<dim3(S, nsets), 256, 0, stream>>>(partial, ysum, eff_modes, plocal, S, C, h, cap_rows, protos);
+    PSAM_CHECK_LAUNCH("k_global_final");
+    return PSAM_OK;
+}
+
+extern "C" int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, int vw, float thresh, int mode,
+                                   float* out, psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(pooled && out, "psam_alp_proto_grid: null pointer");
+    PSAM_CHECK_ARG(S >= 1 && gh >= 0 && gw >= 0 && vw >= 1, "psam_alp_proto_grid: bad shape");
+    PSAM_CHECK_ARG(mode == PSAM_MODE_GRIDCONV || mode == PSAM_MODE_GRIDCONV_PLUS, "psam_alp_proto_grid: grid modes only");
+    size_t N = (size_t)S * gh * gw;
+    if (N == 0 || gh * vw * gw * vw == 0) return PSAM_OK;
+    PSAM_CHECK_ARG(N * sizeof(int32_t) <= 200 * 1024, "psam_alp_proto_grid: grid too large");
+    size_t smem = N * sizeof(int32_t);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(k_proto_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_proto_grid<<<1, 256, smem, stream>>>(pooled, S, gh, gw, vw, thresh, mode, out, nullptr);
+    PSAM_CHECK_LAUNCH("k_proto_grid");
+    return PSAM_OK;
+}

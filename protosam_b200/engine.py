@@ -1,0 +1,162 @@
+"""Batched volume driver: support prototypes once per volume, then every query slice x label in
+three launches, sharded over GPUs.
+
+The reference processes one query slice and one label per Python iteration
+(validation_protosam.py:352-388) and recomputes the same support prototypes for every slice
+(grid_proto_fewshot.py:181-184, 239-259).  Here:
+
+  set_support()  kernel 1 once per volume for the 2L prototype sets (bg_l 'gridconv', fg_l decided on
+                 the device like grid_proto_fewshot.py:250-256) -- on rank 0, then ONE broadcast
+  run()          kernel 2 over the rank's query slices against all sets (one launch), kernel 3a/3b
+                 over the resulting [Q_local*L, 2, h, w] coarse maps (two launches)
+  gather         ONE gather of the fixed-size prompt headers/records
+
+Query slices are independent given the prototypes, so the only exchanges are that broadcast and
+that gather.  No host synchronisation happens between set_support() and the
+final device->host read of the records.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops, prompts as P
+
+FG_THRESH = BG_THRESH = 0.95      # models/grid_proto_fewshot.py:21-22
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of n items owned by `rank` (earlier ranks take the remainder)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+_PROTO_KEYS = ("protos", "counts", "eff_modes", "status")
+
+
+def broadcast_prototypes(protos: dict, src: int = 0, group=None) -> dict:
+    """Broadcast the packed prototype tables from `src` (NCCL over NVLink on the GPU box; the same
+    code runs over gloo in the CPU tests).  Shapes are rank-independent, so receivers pre-allocate."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return protos
+    for k in _PROTO_KEYS:
+        dist.broadcast(protos[k], src=src, group=group)
+    return protos
+
+
+def gather_records(hdr: torch.Tensor, recs: torch.Tensor, counts: Sequence[int], dst: int = 0, group=None):
+    """Gather per-rank (hdr [n_r,64], recs [n_r,max_cc,96]) to `dst` in rank order.  `counts` = images
+    per rank (known from shard_range, no size exchange needed).  Returns (hdr_all, recs_all) on dst,
+    (None, None) elsewhere."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return hdr, recs
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nmax = max(counts)
+
+    def pad(t):
+        if t.shape[0] == nmax:
+            return t.contiguous()
+        out = t.new_zeros((nmax,) + tuple(t.shape[1:]))
+        out[: t.shape[0]] = t
+        return out
+
+    outs = []
+    for t in (hdr, recs):
+        tp = pad(t)
+        bucket = [torch.empty_like(tp) for _ in range(world)] if rank == dst else None
+        dist.gather(tp, bucket, dst=dst, group=group)
+        outs.append(torch.cat([b[:c] for b, c in zip(bucket, counts)], 0) if rank == dst else None)
+    return outs[0], outs[1]
+
+
+class CoarseVolumeEngine:
+    """ALP match + prompt extraction for one volume on this rank's GPU."""
+
+    def __init__(self, feature_hw: Sequence[int], img_size: int, out_size: int = 1024, val_wsize: int = 2,
+                 proto_grid_size: int = 8, use_cca: bool = False, point_mode: str = "both",
+                 max_cc: int = ops.DEFAULT_MAX_CC, max_runs: int = ops.DEFAULT_MAX_RUNS, fg_mode: str = "auto_fg",
+                 match_algo: int = 0, group=None):
+        self.h, self.w = int(feature_hw[0]), int(feature_hw[1])
+        self.img_size, self.out_size = int(img_size), int(out_size)
+        self.val_wsize = int(val_wsize)
+        # MultiProtoAsConv.kernel_size (models/alpmodule.py:34): the window of the fg-mode decision
+        self.kernel_size = (self.h // proto_grid_size, self.w // proto_grid_size)
+        self.use_cca, self.point_mode = bool(use_cca), point_mode
+        self.max_cc, self.max_runs = int(max_cc), int(max_runs)
+        self.fg_mode, self.match_algo, self.group = fg_mode, match_algo, group
+        self.protos: Optional[dict] = None
+        self.n_labels = 0
+        self._ws = None
+
+    # -- distributed helpers -------------------------------------------------------------------
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group), dist.get_rank(self.group)
+        return 1, 0
+
+    # -- support side ----------------------------------------------------------------------------
+    def set_support(self, sup_feats: torch.Tensor, fg_masks: torch.Tensor, src: int = 0):
+        """sup_feats [S,h,w,C] channels-last support features (S = 1, the reference's n_shots);
+        fg_masks [L,S,h,w] foreground masks at feature resolution (nearest-downsampled like
+        grid_proto_fewshot.py:228-231).  Computes on `src`, broadcasts to the other ranks."""
+        S, h, w, C = sup_feats.shape
+        assert (h, w) == (self.h, self.w)
+        if S != 1:
+            raise NotImplementedError("the engine follows the reference configs (n_shots=1); use the "
+                                      "MultiProtoAsConv drop-in for multi-shot support sets")
+        L = fg_masks.shape[0]
+        self.n_labels = L
+        world, rank = self._world()
+        sup_x = sup_feats.permute(0, 3, 1, 2)                      # logical [S,C,h,w], channels-last storage
+        fg = fg_masks.reshape(L, 1, S, h, w).to(torch.float32)
+        sup_y = torch.cat([1.0 - fg, fg], dim=1).reshape(2 * L, S, h, w)   # (bg_0, fg_0, bg_1, fg_1, ...)
+        modes = ["gridconv", self.fg_mode] * L
+        if world == 1 or rank == src:
+            protos = ops.alp_prototypes(sup_x, sup_y, modes, (self.val_wsize, self.val_wsize), FG_THRESH,
+                                        auto_ksize=self.kernel_size)
+        else:
+            gh, gw = h // self.val_wsize, w // self.val_wsize
+            N = S * gh * gw
+            dev = sup_feats.device
+            protos = dict(protos=torch.empty((2 * L, N + S, C), dtype=torch.float32, device=dev),
+                          counts=torch.empty(2 * L, dtype=torch.int32, device=dev),
+                          eff_modes=torch.empty(2 * L, dtype=torch.int32, device=dev),
+                          status=torch.empty(2 * L, dtype=torch.int32, device=dev),
+                          cap_rows=N + S, N=N, gh=gh, gw=gw, S=S, C=C)
+        self.protos = broadcast_prototypes(protos, src=src, group=self.group)
+        return self.protos
+
+    # -- query side ------------------------------------------------------------------------------
+    def match(self, qry_feats: torch.Tensor) -> torch.Tensor:
+        """qry_feats [Q,h,w,C] channels-last -> coarse logits [Q*L, 2, h, w] (bg, fg per label)."""
+        Q, h, w, C = qry_feats.shape
+        scores, _, _ = ops.alp_match(qry_feats.view(Q, h * w, C), self.protos, want_assign=False,
+                                     algo=self.match_algo)
+        return scores.view(Q * self.n_labels, 2, h, w)
+
+    def run(self, qry_feats: torch.Tensor):
+        """-> (hdr uint8 [Q*L,64], recs uint8 [Q*L,max_cc,96]) on the device; image index = q*L + l."""
+        logits = self.match(qry_feats)
+        n = logits.shape[0]
+        need = ops._lib.load().psam_coarse_to_prompts_workspace(n, self.out_size, self.max_runs, self.max_cc)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=qry_feats.device)
+        return ops.coarse_to_prompts(logits, self.img_size, self.out_size, self.use_cca, self.max_cc,
+                                     self.max_runs, workspace=self._ws)
+
+    def run_sharded(self, qry_local: torch.Tensor, q_total: int, dst: int = 0):
+        """This rank's block of a Q-slice volume (see shard_range) -> gathered records on `dst`."""
+        world, _ = self._world()
+        hdr, recs = self.run(qry_local)
+        counts = [(hi - lo) * self.n_labels for lo, hi in (shard_range(q_total, world, r) for r in range(world))]
+        return gather_records(hdr, recs, counts, dst=dst, group=self.group)
+
+    def decode(self, hdr: torch.Tensor, recs: torch.Tensor) -> List[List[P.SlicePrompts]]:
+        """Device records -> per slice, per label prompt objects (one D2H copy)."""
+        H, R = ops.decode_headers(hdr), ops.decode_records(recs)
+        L = self.n_labels
+        flat = [P.prompts_from_records(H[i], R[i], self.use_cca, self.point_mode) for i in range(len(H))]
+        return [flat[q * L:(q + 1) * L] for q in range(len(flat) // L)]

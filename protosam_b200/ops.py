@@ -1,0 +1,185 @@
+"""torch-tensor front-end of the C ABI: allocates outputs/workspaces with torch (plumbing
+only), passes raw device pointers + the current CUDA stream to libpsam_b200.so.
+
+No host synchronisation happens here; every function only enqueues work on
+``torch.cuda.current_stream()``.  Inputs must be CUDA float32 tensors -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MODE_IDS
+
+REC_DTYPE = np.dtype([("box", "<i8", 4), ("conf_pt", "<i8", 2), ("centroid", "<f8", 2), ("conf", "<f8"),
+                      ("conf_pt_p", "<f4"), ("area", "<i4"), ("label", "<i4"), ("flags", "<i4"),
+                      ("reserved", "<i4", 2)])
+HDR_DTYPE = np.dtype([("ncc", "<i4"), ("n_rec", "<i4"), ("n_fg", "<i4"), ("flags", "<i4"),
+                      ("bg_stats", "<i4", 5), ("n_runs", "<i4"), ("bg_centroid", "<f8", 2),
+                      ("selected", "<i4"), ("reserved", "<i4")])
+assert REC_DTYPE.itemsize == 96 and HDR_DTYPE.itemsize == 64
+
+DEFAULT_MAX_CC = 256
+DEFAULT_MAX_RUNS = 65536
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("protosam_b200 runs on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+        if t.dtype != torch.float32 and t.is_floating_point():
+            raise RuntimeError(f"protosam_b200 computes in float32; got {t.dtype}")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------ kernel 1
+
+def alp_prototypes(sup_x, sup_y, modes, ksize, thresh, auto_ksize=None):
+    """sup_x [S,C,h,w] (any strides; channels-last is the fast case), sup_y [nsets,S,h,w],
+    modes: list of 'mask' | 'gridconv' | 'gridconv+' | 'auto_fg'.  Returns a dict of device
+    tensors (see include/psam_b200.h, psam_alp_prototypes)."""
+    L = _lib.load()
+    _need_cuda(sup_x, sup_y)
+    S, C, h, w = sup_x.shape
+    sup_y = sup_y.reshape(-1, S, h, w).contiguous()
+    nsets = sup_y.shape[0]
+    assert len(modes) == nsets
+    kh, kw = int(ksize[0]), int(ksize[1])
+    akh, akw = (int(auto_ksize[0]), int(auto_ksize[1])) if auto_ksize is not None else (kh, kw)
+    gh, gw = h // kh, w // kw
+    N = S * gh * gw
+    cap = N + S
+    dev = sup_x.device
+    out = dict(
+        protos=torch.empty((nsets, cap, C), dtype=torch.float32, device=dev),
+        counts=torch.empty(nsets, dtype=torch.int32, device=dev),
+        eff_modes=torch.empty(nsets, dtype=torch.int32, device=dev),
+        status=torch.empty(nsets, dtype=torch.int32, device=dev),
+        survive=torch.empty((nsets, max(N, 1)), dtype=torch.uint8, device=dev),
+        pooled=torch.empty((nsets, max(N, 1)), dtype=torch.float32, device=dev),
+        cap_rows=cap, N=N, gh=gh, gw=gw, S=S, C=C,
+    )
+    ws = _ws(L.psam_alp_prototypes_workspace(nsets, S, C, h, w, kh, kw), dev)
+    strides = (ctypes.c_int64 * 4)(*sup_x.stride())
+    mode_arr = (ctypes.c_int32 * nsets)(*[MODE_IDS[m] if isinstance(m, str) else int(m) for m in modes])
+    rc = L.psam_alp_prototypes(_ptr(sup_x), strides, _ptr(sup_y), nsets, mode_arr, S, C, h, w, kh, kw, akh, akw,
+                               float(thresh), _ptr(out["protos"]), _ptr(out["counts"]), _ptr(out["eff_modes"]),
+                               _ptr(out["status"]), _ptr(out["survive"]), _ptr(out["pooled"]), _ptr(ws),
+                               ws.numel(), _stream())
+    _lib.check(rc, "psam_alp_prototypes")
+    out["_ws"] = ws          # keep alive until the stream has consumed it
+    return out
+
+
+def alp_proto_grid(pooled_set, S, gh, gw, vw, thresh, mode):
+    """`resized_proto_grid` [1,1,gh*vw,gw*vw] of one set (viz only)."""
+    L = _lib.load()
+    _need_cuda(pooled_set)
+    out = torch.zeros((1, 1, gh * vw, gw * vw), dtype=torch.float32, device=pooled_set.device)
+    rc = L.psam_alp_proto_grid(_ptr(pooled_set), S, gh, gw, vw, float(thresh), MODE_IDS[mode], _ptr(out), _stream())
+    _lib.check(rc, "psam_alp_proto_grid")
+    return out
+
+
+# ------------------------------------------------------------------ kernel 2
+
+def alp_match(qry, protos, want_assign=True, want_sims=False, algo=0):
+    """qry [Q,HW,C] with unit channel stride (rows may be padded / slices strided);
+    protos = dict from alp_prototypes.  Returns (scores [Q,nsets,HW], assign | None, sims | None)."""
+    L = _lib.load()
+    _need_cuda(qry)
+    Q, HW, C = qry.shape
+    if qry.stride(2) != 1:
+        raise RuntimeError("alp_match needs channels-last rows (stride of C == 1)")
+    nsets, cap = protos["protos"].shape[0], protos["cap_rows"]
+    dev = qry.device
+    scores = torch.empty((Q, nsets, HW), dtype=torch.float32, device=dev)
+    assign = torch.empty((Q, nsets, HW), dtype=torch.float32, device=dev) if want_assign else None
+    sims = torch.empty((Q, nsets, cap, HW), dtype=torch.float32, device=dev) if want_sims else None
+    ws = _ws(L.psam_alp_match_workspace(Q, HW, C, nsets, cap, algo), dev)
+    rc = L.psam_alp_match(_ptr(qry), qry.stride(0), qry.stride(1), Q, HW, C, _ptr(protos["protos"]), cap,
+                          _ptr(protos["counts"]), _ptr(protos["eff_modes"]), nsets, _ptr(scores), _ptr(assign),
+                          _ptr(sims), _ptr(protos["status"]), _ptr(ws), ws.numel(), algo, _stream())
+    _lib.check(rc, "psam_alp_match")
+    return scores, assign, sims
+
+
+# ------------------------------------------------------------------ kernel 3
+
+def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False):
+    """logits [n,2,h,w] -> (p_fg [n,out,out] | None, maskbits [n,out,out//32] int32, probs2 | None)."""
+    L = _lib.load()
+    _need_cuda(logits)
+    logits = logits.contiguous()
+    n, two, h, w = logits.shape
+    assert two == 2
+    dev = logits.device
+    p_fg = torch.empty((n, out, out), dtype=torch.float32, device=dev) if want_p_fg else None
+    bits = torch.empty((n, out, out // 32), dtype=torch.int32, device=dev)
+    probs2 = torch.empty((n, 2, out, out), dtype=torch.float32, device=dev) if want_probs2 else None
+    rc = L.psam_upsample_softmax(_ptr(logits), n, h, w, int(mid), int(out), _ptr(p_fg), _ptr(bits), _ptr(probs2),
+                                 _stream())
+    _lib.check(rc, "psam_upsample_softmax")
+    return p_fg, bits, probs2
+
+
+def components(maskbits, p_fg, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DEFAULT_MAX_RUNS, want_labels=False):
+    """-> (hdr uint8 [n,64], recs uint8 [n,max_cc,96], labels int32 [n,out,out] | None), all on device."""
+    L = _lib.load()
+    _need_cuda(p_fg)
+    n, out, _ = p_fg.shape
+    dev = p_fg.device
+    hdr = torch.zeros((n, HDR_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    recs = torch.zeros((n, max_cc, REC_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    labels = torch.empty((n, out, out), dtype=torch.int32, device=dev) if want_labels else None
+    ws = _ws(L.psam_prompts_workspace(n, out, max_runs, max_cc), dev)
+    rc = L.psam_components(_ptr(maskbits), _ptr(p_fg), n, out, int(bool(use_cca)), max_cc, max_runs, _ptr(hdr),
+                           _ptr(recs), _ptr(labels), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "psam_components")
+    return hdr, recs, labels
+
+
+def coarse_to_prompts(logits, mid, out=1024, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DEFAULT_MAX_RUNS,
+                      workspace=None):
+    """logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on device, one call."""
+    L = _lib.load()
+    _need_cuda(logits)
+    logits = logits.contiguous()
+    n, two, h, w = logits.shape
+    assert two == 2
+    dev = logits.device
+    hdr = torch.zeros((n, HDR_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    recs = torch.zeros((n, max_cc, REC_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    need = L.psam_coarse_to_prompts_workspace(n, out, max_runs, max_cc)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
+    rc = L.psam_coarse_to_prompts(_ptr(logits), n, h, w, int(mid), int(out), int(bool(use_cca)), max_cc, max_runs,
+                                  _ptr(hdr), _ptr(recs), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "psam_coarse_to_prompts")
+    return hdr, recs
+
+
+def decode_headers(hdr_u8) -> np.ndarray:
+    """device/host uint8 [n,64] -> numpy structured array (host sync on .cpu())."""
+    return np.frombuffer(hdr_u8.detach().cpu().numpy().tobytes(), dtype=HDR_DTYPE)
+
+
+def decode_records(recs_u8) -> np.ndarray:
+    a = recs_u8.detach().cpu().numpy()
+    return np.frombuffer(a.tobytes(), dtype=REC_DTYPE).reshape(a.shape[0], a.shape[1])

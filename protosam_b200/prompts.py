@@ -1,0 +1,168 @@
+"""Host-side mirror of the reference's coarse-mask -> SAM-prompt helpers.
+
+The reference runs this stage on the CPU with OpenCV/numpy (util/utils.py:474-541,
+models/ProtoSAM.py:242-289, 349-450, 592-635).  Here kernel 3 (libpsam_b200.so) does the work on
+the GPU and emits compact records; this module only re-packages those records into the exact
+objects the reference hands to ``SamPredictor.predict`` (models/ProtoSAM.py:500-533): same names,
+argument meaning, dtypes and shapes.  No arithmetic on the maps happens in Python.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+CONF_MODE, CENTROID_MODE, BOTH_MODE = "conf", "centroid", "both"
+POINT_MODES = (CONF_MODE, CENTROID_MODE, BOTH_MODE)
+
+
+class ConnectedComponents(tuple):
+    """The cv2-style 4-tuple ``(n, labels, stats, centroids)`` the reference's helpers pass around
+    (util/utils.py:478), carrying the GPU records it was built from."""
+
+    def __new__(cls, n, labels, stats, centroids, records=None, header=None):
+        self = super().__new__(cls, (n, labels, stats, centroids))
+        self.records = records
+        self.header = header
+        return self
+
+
+@dataclass
+class SlicePrompts:
+    """Everything ProtoSAM.forward derives for one (query slice, label) before calling SAM."""
+    empty: bool                      # ProtoSAM.py:612-613 early return
+    ncc: int                         # components found
+    boxes: Optional[np.ndarray]      # int64 [n,4] XYXY           get_bbox_per_cc
+    points: Optional[np.ndarray]     # [n,npts,2] int64|float64   get_sam_input_points
+    point_labels: Optional[np.ndarray]
+    conf: Optional[dict]             # {label: confidence}, None with use_cca
+    multimask_output: bool           # ProtoSAM.py:522
+    flags: int
+
+    def predict_calls(self) -> List[dict]:
+        """kwargs of each SamPredictor.predict call, as predict_w_points_bbox builds them (:505-523)."""
+        if self.empty:
+            return []
+        return [dict(point_coords=self.points[i], point_labels=np.array([1] * len(self.points[i])),
+                     box=self.boxes[i], multimask_output=self.multimask_output)
+                for i in range(len(self.boxes))]
+
+
+def _points_from_records(recs: np.ndarray, point_mode: str) -> np.ndarray:
+    if point_mode == CONF_MODE:
+        return recs["conf_pt"][:, None, :].astype(np.int64)                       # [n,1,2] int64
+    if point_mode == CENTROID_MODE:
+        return recs["centroid"][:, None, :].astype(np.float64)                    # [n,1,2] float64
+    if point_mode == BOTH_MODE:                                                   # np.vstack -> float64
+        return np.stack([recs["conf_pt"].astype(np.float64), recs["centroid"]], axis=1)
+    raise NotImplementedError(f"point mode {point_mode} not implemented")
+
+
+def prompts_from_records(hdr: np.void, recs: np.ndarray, use_cca: bool, point_mode: str = BOTH_MODE) -> SlicePrompts:
+    """One image's header + records -> the reference's prompt arrays."""
+    if point_mode not in POINT_MODES:
+        raise ValueError(f"point mode must be one of {POINT_MODES}")
+    flags = int(hdr["flags"])
+    if flags & _lib.IMG_RUN_OVERFLOW:
+        raise RuntimeError("coarse mask has more foreground runs than the workspace holds; "
+                           "re-run with a larger max_runs")
+    if flags & _lib.IMG_EMPTY:
+        return SlicePrompts(True, 0, None, None, None, None, not use_cca, flags)
+    n = int(hdr["n_rec"])
+    r = recs[:n]
+    pts = _points_from_records(r, point_mode)
+    labels = np.array([l + 1 for l, p in enumerate(pts) for _ in range(len(p))])
+    conf = None
+    if not use_cca:
+        conf = {0: 0}
+        conf.update({int(lab): float(c) for lab, c in zip(r["label"], r["conf"])})
+    return SlicePrompts(False, int(hdr["ncc"]), r["box"].astype(np.int64).copy(), pts, labels, conf,
+                        not use_cca, flags)
+
+
+def coarse_to_prompts(low_logits: torch.Tensor, mid_size: int, out_size: int = 1024, use_cca: bool = False,
+                      point_mode: str = BOTH_MODE, max_cc: int = ops.DEFAULT_MAX_CC,
+                      max_runs: int = ops.DEFAULT_MAX_RUNS) -> List[SlicePrompts]:
+    """[n,2,h,w] coarse scores (CUDA) -> prompts per image.  Mirrors FewShotSeg's upsample
+    (grid_proto_fewshot.py:270-273) + ProtoSAM.forward lines 592-635."""
+    hdr, recs = ops.coarse_to_prompts(low_logits, mid_size, out_size, use_cca, max_cc, max_runs)
+    H, R = ops.decode_headers(hdr), ops.decode_records(recs)           # one D2H of ~n*(64+96*max_cc) bytes
+    return [prompts_from_records(H[i], R[i], use_cca, point_mode) for i in range(len(H))]
+
+
+# ---------------------------------------------------------------------------------------------
+# Function-level drop-ins with the reference's names and return conventions.
+# ---------------------------------------------------------------------------------------------
+
+def _cc_from_full_logits(query_pred_logits: torch.Tensor, use_cca: bool, max_cc: int, max_runs: int):
+    ops._need_cuda(query_pred_logits)
+    assert query_pred_logits.dim() == 4 and query_pred_logits.shape[0] == 1 and query_pred_logits.shape[1] == 2
+    S = query_pred_logits.shape[-1]
+    p_fg, bits, _ = ops.upsample_softmax(query_pred_logits, S, S)
+    hdr, recs, labels = ops.components(bits, p_fg, use_cca, max_cc, max_runs, want_labels=True)
+    H, R = ops.decode_headers(hdr)[0], ops.decode_records(recs)[0]
+    if int(H["flags"]) & _lib.IMG_RUN_OVERFLOW:
+        raise RuntimeError("more foreground runs than max_runs")
+    if int(H["flags"]) & _lib.IMG_CC_TRUNCATED:
+        raise RuntimeError(f"{int(H['ncc'])} components exceed max_cc={max_cc}")
+    r = R[: int(H["n_rec"])]
+    n = len(r) + 1
+    stats = np.zeros((n, 5), np.int32)
+    cent = np.zeros((n, 2), np.float64)
+    stats[0] = H["bg_stats"]
+    cent[0] = H["bg_centroid"]
+    stats[1:, 0] = r["box"][:, 0]
+    stats[1:, 1] = r["box"][:, 1]
+    stats[1:, 2] = r["box"][:, 2] - r["box"][:, 0] + 1
+    stats[1:, 3] = r["box"][:, 3] - r["box"][:, 1] + 1
+    stats[1:, 4] = r["area"]
+    cent[1:] = r["centroid"]
+    return ConnectedComponents(n, labels[0].cpu().numpy(), stats, cent, records=r, header=H)
+
+
+def get_connected_components(query_pred_original, query_pred_logits, return_conf=False,
+                             max_cc=4096, max_runs=ops.DEFAULT_MAX_RUNS):
+    """util/utils.py:474-494.  ``query_pred_logits`` [1,2,H,W] CUDA logits at full resolution; the
+    mask is re-derived from them on the device (identical to ``query_pred_original`` by
+    construction: it is their argmax)."""
+    cc = _cc_from_full_logits(query_pred_logits, False, max_cc, max_runs)
+    if not return_conf:
+        return cc, None
+    conf = {0: 0}
+    conf.update({int(l): float(c) for l, c in zip(cc.records["label"], cc.records["conf"])})
+    return cc, conf
+
+
+def cca(query_pred_original, query_pred_logits, return_conf=False, return_cc=False,
+        max_runs=ops.DEFAULT_MAX_RUNS):
+    """util/utils.py:496-541: keep the most confident component."""
+    cc = _cc_from_full_logits(query_pred_logits, True, 1, max_runs)
+    if return_cc:
+        return cc
+    pred = np.asarray(query_pred_original.detach().cpu() if torch.is_tensor(query_pred_original)
+                      else query_pred_original)
+    if cc[0] < 2:
+        out, max_conf = np.zeros_like(pred), 0
+    else:
+        out, max_conf = pred * (cc[1] == 1).astype(np.uint8), float(cc.records["conf"][0])
+    return (out, max_conf) if return_conf else out
+
+
+def get_bbox_per_cc(conn_components: ConnectedComponents) -> np.ndarray:
+    """models/ProtoSAM.py:242-264 -> int64 [n-1,4] XYXY inclusive."""
+    return conn_components.records["box"].astype(np.int64).copy()
+
+
+def get_sam_input_points(conn_components: ConnectedComponents, output_p=None, get_neg_points=False, l=1,
+                         point_mode=BOTH_MODE):
+    """models/ProtoSAM.py:349-450 (num_points_for_sam = 1, get_neg_points=False)."""
+    if get_neg_points:
+        raise NotImplementedError("negative points are off in the reference configs (config_ssl_upload.py:102)")
+    pts = _points_from_records(conn_components.records, point_mode)
+    labels = np.array([k + 1 for k, p in enumerate(pts) for _ in range(len(p))])
+    neg = [None for _ in range(len(pts))]
+    return pts, labels, neg, np.array([0] * len(neg))

@@ -1,0 +1,90 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo processes exercise the
+prototype broadcast, the slice sharding and the prompt-record gather of protosam_b200.engine."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from protosam_b200 import engine, ops, prompts
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q_total, L, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1) broadcast of the packed prototype tables (rank 0 holds the real ones)
+        nsets, cap, C = 2 * L, 9, 16
+        g = torch.Generator().manual_seed(5)
+        truth = dict(protos=torch.randn(nsets, cap, C, generator=g),
+                     counts=torch.arange(nsets, dtype=torch.int32), eff_modes=torch.ones(nsets, dtype=torch.int32),
+                     status=torch.zeros(nsets, dtype=torch.int32))
+        mine = {k: (v.clone() if rank == 0 else torch.zeros_like(v)) for k, v in truth.items()}
+        engine.broadcast_prototypes(mine, src=0)
+        ok_bcast = all(torch.equal(mine[k], truth[k]) for k in truth)
+        # 2) shard + gather of fixed-size records, ragged split (q_total not divisible by world)
+        lo, hi = engine.shard_range(q_total, world, rank)
+        n_local = (hi - lo) * L
+        max_cc = 3
+        hdr = np.zeros(n_local, ops.HDR_DTYPE)
+        recs = np.zeros((n_local, max_cc), ops.REC_DTYPE)
+        for i in range(n_local):
+            gi = lo * L + i
+            hdr["ncc"][i] = hdr["n_rec"][i] = 1 + gi % max_cc
+            recs["label"][i, : 1 + gi % max_cc] = np.arange(1, 2 + gi % max_cc)
+            recs["box"][i, :, 0] = gi
+            recs["centroid"][i, :, 0] = gi + 0.5
+        th = torch.from_numpy(hdr.view(np.uint8).reshape(n_local, 64).copy())
+        tr = torch.from_numpy(recs.view(np.uint8).reshape(n_local, max_cc, 96).copy())
+        counts = [(b - a) * L for a, b in (engine.shard_range(q_total, world, r) for r in range(world))]
+        H, R = engine.gather_records(th, tr, counts, dst=0)
+        if rank == 0:
+            Hn, Rn = ops.decode_headers(H), ops.decode_records(R)
+            ok = len(Hn) == q_total * L
+            for gi in range(q_total * L):
+                ok &= int(Hn["n_rec"][gi]) == 1 + gi % max_cc and int(Rn["box"][gi, 0, 0]) == gi
+                ok &= float(Rn["centroid"][gi, 0, 0]) == gi + 0.5
+                sp = prompts.prompts_from_records(Hn[gi], Rn[gi], use_cca=False, point_mode="both")
+                ok &= len(sp.predict_calls()) == 1 + gi % max_cc
+            out_q.put((ok_bcast, bool(ok)))
+        else:
+            assert H is None and R is None
+            out_q.put((ok_bcast, True))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("q_total", [4, 5])
+def test_broadcast_shard_gather_world2(q_total):
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q_total, 2, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out_q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(a and b for a, b in res)
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 32, 1024):
+        for world in (1, 2, 3, 8):
+            blocks = [engine.shard_range(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1

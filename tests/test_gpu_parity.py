@@ -1,0 +1,327 @@
+"""Parity of the CUDA path (through the C ABI, ctypes) with the reference-generated golden fixtures
+and with the CPU oracle.  Bars (BASELINE.json north_star): survival masks, component counts,
+argmax points, boxes, centroids bit-exact; similarity / prediction maps within 1e-3 absolute."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+from protosam_b200 import _lib, ops, prompts as PR, synth  # noqa: E402
+from protosam_b200.alpmodule import MultiProtoAsConv  # noqa: E402
+from protosam_b200.engine import CoarseVolumeEngine  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MAP_TOL = 1e-3
+DEV = "cuda:0"
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# ------------------------------------------------------------------------------ ALP module
+
+@pytest.mark.parametrize("n", list(_load("alp_small.npz")["names"]))
+def test_alp_module_vs_reference_golden(n, capsys):
+    g = _load("alp_small.npz")
+    mode, isval, vw, pg, thresh, q5d = g[f"{n}/meta"]
+    isval, vw, pg, thresh = bool(int(isval)), (None if vw == "None" else int(vw)), int(pg), float(thresh)
+    sup, qry, y = g[f"{n}/sup"], g[f"{n}/qry"], g[f"{n}/y"]
+    S, h, w, C = sup.shape
+    m = MultiProtoAsConv(proto_grid=[pg, pg], feature_hw=[h, w])
+    assert len(list(m.parameters())) == 0 and len(m.state_dict()) == 0
+    sup_x = _t(sup).permute(0, 3, 1, 2)[None, :, None]              # channels-last storage like the caller's
+    q = _t(qry).permute(2, 0, 1)[None, None]
+    if not int(q5d):
+        q = q[:, 0]
+    sup_y = _t(y)[None, :, None]
+    with torch.no_grad():
+        if f"{n}/error" in g.files:
+            with pytest.raises(RuntimeError):
+                m(q, sup_x, sup_y, mode, thresh, isval=isval, val_wsize=vw, vis_sim=True)
+            assert "failed to find prototypes" in capsys.readouterr().out
+            return
+        pred, assign, vis, grid = m(q, sup_x, sup_y, mode, thresh, isval=isval, val_wsize=vw, vis_sim=True)
+    assert tuple(pred.shape) == g[f"{n}/pred_grid"].shape
+    assert tuple(assign[0].shape) == g[f"{n}/debug_assign"].shape
+    assert tuple(grid.shape) == g[f"{n}/proto_grid"].shape
+    np.testing.assert_allclose(pred.cpu().numpy(), g[f"{n}/pred_grid"], atol=MAP_TOL, rtol=0)
+    sims = vis["raw_local_sims"].cpu().numpy()
+    assert sims.shape == g[f"{n}/raw_local_sims"].shape
+    np.testing.assert_allclose(sims, g[f"{n}/raw_local_sims"], atol=MAP_TOL, rtol=0)
+    assert np.array_equal(grid.cpu().numpy(), g[f"{n}/proto_grid"])
+    assert vis["proto_assign"] is assign[0]
+    if mode == "mask":
+        np.testing.assert_allclose(assign[0].cpu().numpy(), g[f"{n}/debug_assign"], atol=MAP_TOL, rtol=0)
+        return
+    # argmax may differ only where two similarities tie within fp32 noise
+    a, ra = assign[0].cpu().numpy(), g[f"{n}/debug_assign"]
+    bad = np.argwhere(a != ra)
+    for (b, yy, xx) in bad:
+        s = g[f"{n}/raw_local_sims"][b, :, yy, xx]
+        assert abs(s[int(a[b, yy, xx])] - s[int(ra[b, yy, xx])]) < 1e-4
+    # survival mask: bit-exact gate
+    ks = (vw, vw) if isval else (h // pg, w // pg)
+    pr = ops.alp_prototypes(_t(sup).permute(0, 3, 1, 2), _t(y)[None], [mode], ks, thresh)
+    N = pr["N"]
+    assert np.array_equal(pr["survive"][0, :N].cpu().numpy().astype(bool), g[f"{n}/survive"])
+    P = int(pr["counts"][0])
+    assert P == g[f"{n}/pro_n"].shape[0]
+    np.testing.assert_allclose(pr["protos"][0, :P].cpu().numpy(), g[f"{n}/pro_n"], atol=1e-5, rtol=0)
+
+
+def test_alp_module_rejects_cpu_and_grad():
+    m = MultiProtoAsConv([8, 8], [16, 16])
+    q = torch.zeros(1, 1, 8, 16, 16)
+    sx = torch.zeros(1, 1, 1, 8, 16, 16)
+    sy = torch.ones(1, 1, 1, 16, 16)
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        m(q, sx, sy, "gridconv+", 0.95)                           # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        m(q, sx, sy, "bogus", 0.95)
+    with pytest.raises(RuntimeError):
+        m(q.to(DEV).requires_grad_(True), sx.to(DEV), sy.to(DEV), "gridconv+", 0.95)
+
+
+def test_alp_contiguous_nchw_query_and_batched_queries():
+    """NCHW-contiguous inputs (not channels-last) and several query slices in one call."""
+    vol = synth.make_volume(3, Q=3, L=1, C=64, h=16, w=16, img_size=128)
+    m = MultiProtoAsConv([8, 8], [16, 16])
+    sx = _t(np.transpose(vol.sup, (0, 3, 1, 2)))[None, :, None]     # truly NCHW contiguous
+    q = _t(np.transpose(vol.qry, (0, 3, 1, 2)))                      # [3,C,h,w]
+    with torch.no_grad():
+        pred, _, _, _ = m(q, sx, _t(vol.fg[0])[None, :, None], "gridconv+", 0.95, isval=True, val_wsize=2)
+    for i in range(3):
+        ref, _, _, _ = O.alp_forward(np.transpose(vol.qry[i], (2, 0, 1))[None], np.transpose(vol.sup, (0, 3, 1, 2))[None, :, None],
+                                     vol.fg[0][None, :, None], "gridconv+", 0.95, [2, 2], isval=True, val_wsize=2)
+        np.testing.assert_allclose(pred[i].cpu().numpy(), ref[0], atol=MAP_TOL, rtol=0)
+
+
+@pytest.mark.parametrize("cfg_name", ["cfg1_vits_256", "cfg2_chaos_mri"])
+def test_engine_match_vs_reference_golden(cfg_name):
+    """Batched engine (all labels, all slices, bg+fg sets in one launch) vs per-call reference outputs."""
+    g = _load("alp_configs.npz")
+    seed, nq, L = [int(v) for v in g[f"{cfg_name}/meta"]]
+    cfg = synth.CONFIGS[cfg_name]
+    vol = synth.make_volume(seed, Q=nq, L=L, C=cfg["C"], h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    for fg_mode, kind in (("gridconv+", "fg"), ("mask", "fgmask")):
+        eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"], fg_mode=fg_mode)
+        pr = eng.set_support(_t(vol.sup), _t(vol.fg))
+        logits = eng.match(_t(vol.qry)).cpu().numpy()               # [Q*L,2,h,w]
+        N = pr["N"]
+        for l in range(L):
+            for name, si in (("bg", 2 * l), (kind, 2 * l + 1)):
+                if name != "fgmask":
+                    assert np.array_equal(pr["survive"][si, :N].cpu().numpy().astype(bool), g[f"{cfg_name}/l{l}/q0/{name}/survive"])
+                for q in range(nq):
+                    ref = g[f"{cfg_name}/l{l}/q{q}/{name}/pred_grid"][0, 0]
+                    np.testing.assert_allclose(logits[q * L + l, si % 2], ref, atol=MAP_TOL, rtol=0)
+
+
+def test_engine_auto_fg_mode_matches_caller_rule():
+    """grid_proto_fewshot.py:254-256: 'gridconv+' iff some kernel_size window is >= 0.95 foreground."""
+    h = w = 32
+    fg = np.zeros((3, 1, h, w), np.float32)
+    fg[0, 0, 4:8, 4:8] = 1          # exactly one full 4x4 training window -> gridconv+
+    fg[1, 0, 5:9, 5:9] = 1          # 4x4 blob straddling windows -> no full window -> mask
+    fg[2, 0, 10, 10] = 1            # single pixel -> mask
+    sup = synth.layer_norm(synth.gaussian_like(1, (1, h, w, 32)))
+    eng = CoarseVolumeEngine((h, w), 256, val_wsize=2, proto_grid_size=8)
+    pr = eng.set_support(_t(sup), _t(fg))
+    eff = pr["eff_modes"].cpu().numpy()
+    assert [_lib.MODE_NAMES[int(e)] for e in eff] == ["gridconv", "gridconv+", "gridconv", "mask", "gridconv", "mask"]
+    counts = pr["counts"].cpu().numpy()
+    assert counts[1] == 4 + 1 and counts[3] == 1 and counts[5] == 1
+
+
+# ------------------------------------------------------------------------------ prompts
+
+def _prompt_cases():
+    return list(_load("prompts.npz")["names"])
+
+
+@pytest.mark.parametrize("key", _prompt_cases())
+def test_prompts_vs_reference_golden(key):
+    """What ProtoSAM.forward hands to SamPredictor.predict, bit for bit (dtype included)."""
+    g = _load("prompts.npz")
+    name, cfg = key.split("/")
+    use_cca, pm = cfg.startswith("cca1"), cfg.split("_", 1)[1]
+    low, S = g[f"{name}/low"], int(g[f"{name}/S"])
+    sp = PR.coarse_to_prompts(_t(low), S, 1024, use_cca=use_cca, point_mode=pm, max_cc=512)[0]
+    calls = sp.predict_calls()
+    assert len(calls) == int(g[f"{key}/ncalls"])
+    if not calls:
+        return
+    pts = np.stack([c["point_coords"] for c in calls])
+    assert pts.dtype == g[f"{key}/points"].dtype and np.array_equal(pts, g[f"{key}/points"])
+    assert np.array_equal(np.stack([c["box"] for c in calls]), g[f"{key}/boxes"])
+    assert np.array_equal(np.stack([c["point_labels"] for c in calls]), g[f"{key}/point_labels"])
+    assert all(c["multimask_output"] == bool(m) for c, m in zip(calls, g[f"{key}/multimask"]))
+
+
+@pytest.mark.parametrize("name", sorted({k.split("/")[0] for k in _prompt_cases()}))
+def test_upsample_softmax_bits_vs_reference_golden(name):
+    g = _load("prompts.npz")
+    low, S = g[f"{name}/low"], int(g[f"{name}/S"])
+    p_fg, bits, probs2 = ops.upsample_softmax(_t(low), S, 1024, want_probs2=True)
+    mask = np.unpackbits(bits[0].cpu().numpy().view(np.uint8), bitorder="little").reshape(1024, 1024)
+    assert np.array_equal(np.packbits(mask), g[f"{name}/pred_bits"])
+    assert np.array_equal(p_fg[0].cpu().numpy()[::61, ::67], g[f"{name}/p_fg_sample"])
+    assert torch.equal(probs2[0, 1], p_fg[0])
+
+
+@pytest.mark.parametrize("h,S,out", [(32, 256, 1024), (37, 518, 1024), (48, 672, 1024), (73, 1024, 1024),
+                                     (24, 96, 256), (16, 64, 64)])
+def test_upsample_softmax_full_map_vs_oracle(h, S, out):
+    """every pixel of p (both channels) equals the oracle's ATen-CPU restatement"""
+    low = (synth.gaussian_like(h * 7 + S, (3, 2, h, h)) * 9).astype(np.float32)
+    p_fg, bits, probs2 = ops.upsample_softmax(_t(low), S, out, want_probs2=True)
+    for i in range(3):
+        _, p, pred = O.coarse_logits_to_probs(low[i:i + 1], S, out)
+        assert np.array_equal(probs2[i].cpu().numpy(), p[0])
+        mask = np.unpackbits(bits[i].cpu().numpy().view(np.uint8), bitorder="little").reshape(out, out)
+        assert np.array_equal(mask, pred)
+
+
+def test_full_resolution_logits_path():
+    lg = (synth.gaussian_like(11, (1, 2, 256, 256)) * 6).astype(np.float32)
+    p_fg, bits, probs2 = ops.upsample_softmax(_t(lg), 256, 256, want_probs2=True)
+    assert np.array_equal(probs2.cpu().numpy(), O.softmax2(lg))
+
+
+def _pack(mask):
+    return torch.from_numpy(np.packbits(mask.astype(np.uint8), axis=-1, bitorder="little").view(np.int32)).to(DEV)
+
+
+@pytest.mark.parametrize("out,density,seed", [(64, 0.5, 0), (256, 0.4, 1), (1024, 0.45, 2), (1024, 0.6, 3),
+                                              (1024, 0.02, 4), (1024, 0.98, 5)])
+def test_components_vs_oracle_noise_masks(out, density, seed):
+    """pixel-noise masks (up to ~70k components): labels, order, stats, centroids, points, confidences"""
+    rng = np.random.default_rng(seed)
+    mask = rng.random((out, out)) < density
+    p = (0.5 + rng.integers(0, 1 << 23, (out, out)) * 2.0 ** -24).astype(np.float32)
+    p[rng.random((out, out)) < 0.3] = 1.0                              # many ties at the maximum
+    n, lab, st, ce = O.connected_components(mask)
+    hdr, recs, labels = ops.components(_pack(mask)[None], _t(p)[None], use_cca=False, max_cc=1 << 17,
+                                       max_runs=out * out // 2 + 1, want_labels=True)
+    H, R = ops.decode_headers(hdr)[0], ops.decode_records(recs)[0]
+    assert int(H["flags"]) == 0 and int(H["ncc"]) == n - 1 and int(H["n_fg"]) == int(mask.sum())
+    assert np.array_equal(labels[0].cpu().numpy(), lab)
+    R = R[: n - 1]
+    assert np.array_equal(R["label"], np.arange(1, n))
+    assert np.array_equal(R["area"], st[1:, 4])
+    assert np.array_equal(R["box"][:, 0], st[1:, 0]) and np.array_equal(R["box"][:, 1], st[1:, 1])
+    assert np.array_equal(R["box"][:, 2] - R["box"][:, 0] + 1, st[1:, 2])
+    assert np.array_equal(R["centroid"], ce[1:])
+    assert np.array_equal(H["bg_stats"], st[0]) and np.array_equal(H["bg_centroid"], ce[0])
+    bbox, pt, val = O._cc_prompts(p, lab, n)
+    assert np.array_equal(R["box"], bbox[1:])
+    assert np.array_equal(R["conf_pt"], pt[1:])                        # incl. torch.topk's n<64 tie rule
+    assert np.array_equal(R["conf_pt_p"], val[1:])
+    sums = O.cc_sums(p, lab, n).astype(np.float64)[1:] / (mask.sum() + 1e-6)
+    np.testing.assert_allclose(R["conf"], sums, rtol=1e-5)
+
+
+def test_components_use_cca_selects_oracle_component():
+    rng = np.random.default_rng(9)
+    for t in range(4):
+        low = (rng.random((20, 20)) < 0.25).astype(np.float32)
+        up = torch.nn.functional.interpolate(torch.from_numpy(low)[None, None], size=(512, 512), mode="bilinear")[0, 0].numpy()
+        mask = up > 0.35
+        p = (0.5 + np.minimum(up, 1.0) * 0.4999).astype(np.float32)
+        cc = O.cca(mask.astype(np.uint8), p, return_cc=True)
+        hdr, recs, labels = ops.components(_pack(mask)[None], _t(p)[None], use_cca=True, max_cc=1, want_labels=True)
+        H, R = ops.decode_headers(hdr)[0], ops.decode_records(recs)[0]
+        assert int(H["n_rec"]) == 1 and np.array_equal(labels[0].cpu().numpy(), cc[1])
+        assert np.array_equal(R[0]["centroid"], cc[3][1]) and int(R[0]["area"]) == cc[2][1, 4]
+
+
+def test_run_table_overflow_is_reported():
+    mask = np.zeros((256, 256), bool)
+    mask[:, ::2] = True
+    hdr, _, _ = ops.components(_pack(mask)[None], _t(np.full((256, 256), 0.75, np.float32))[None], max_runs=1000)
+    H = ops.decode_headers(hdr)[0]
+    assert int(H["flags"]) & _lib.IMG_RUN_OVERFLOW
+    with pytest.raises(RuntimeError):
+        PR.prompts_from_records(H, None, False)
+
+
+def test_function_level_dropins_match_oracle():
+    lg = (torch.nn.functional.interpolate(torch.from_numpy(synth.gaussian_like(21, (1, 2, 9, 9)) * 9), size=(512, 512),
+                                          mode="bicubic")).numpy().astype(np.float32)
+    p = O.softmax2(lg)
+    pred = (p[0, 1] > p[0, 0]).astype(np.uint8)
+    cc, conf = PR.get_connected_components(pred, _t(lg), return_conf=True)
+    rcc, rconf = O.get_connected_components(pred, p[0, 1], return_conf=True)
+    assert cc[0] == rcc[0] and np.array_equal(cc[1], rcc[1]) and np.array_equal(cc[2], rcc[2]) and np.array_equal(cc[3], rcc[3])
+    for k in rconf:
+        assert conf[k] == pytest.approx(float(rconf[k]), rel=1e-5)
+    assert np.array_equal(PR.get_bbox_per_cc(cc), O.get_bbox_per_cc(rcc))
+    for pm in ("conf", "centroid", "both"):
+        pts, labels, _, _ = PR.get_sam_input_points(cc, None, point_mode=pm)
+        rpts, rlabels = O.get_sam_input_points(rcc, p[0, 1], pm)
+        assert pts.dtype == rpts.dtype and np.array_equal(pts, rpts) and np.array_equal(labels, rlabels)
+    sel = PR.cca(pred, _t(lg), return_cc=True)
+    rsel = O.cca(pred, p[0, 1], return_cc=True)
+    assert sel[0] == rsel[0] and np.array_equal(sel[1], rsel[1]) and np.array_equal(sel[3], rsel[3])
+    assert np.array_equal(PR.cca(pred, _t(lg)), O.cca(pred, p[0, 1]))
+
+
+# ------------------------------------------------------------------------------ whole path
+
+@pytest.mark.parametrize("cfg_name,nq", [("cfg1_vits_256", 1), ("cfg2_chaos_mri", 3), ("cfg3_synapse_ct", 2)])
+@pytest.mark.parametrize("use_cca", [False, True])
+def test_engine_end_to_end_vs_oracle(cfg_name, nq, use_cca):
+    """features -> prompts on the device vs the oracle run stage by stage on the same inputs."""
+    cfg = synth.CONFIGS[cfg_name]
+    L = min(cfg["L"], 2)
+    vol = synth.make_volume(4321, Q=nq, L=L, C=cfg["C"], h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"], use_cca=use_cca)
+    eng.set_support(_t(vol.sup), _t(vol.fg))
+    q = _t(vol.qry)
+    logits = eng.match(q).cpu().numpy()
+    got = eng.decode(*eng.run(q))
+    for qi in range(nq):
+        for l in range(L):
+            ref = O.coarse_to_prompts(logits[qi * L + l][None], cfg["img_size"], 1024, use_cca=use_cca, point_mode="both")
+            s = got[qi][l]
+            assert s.empty == ref["empty"]
+            if s.empty:
+                continue
+            assert np.array_equal(s.boxes, ref["bboxes"])
+            assert np.array_equal(s.points, ref["points"]) and s.points.dtype == ref["points"].dtype
+            assert np.array_equal(s.point_labels, ref["point_labels"])
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE config 2 at full size (32 slices x 4 labels): size-independent properties."""
+    cfg = synth.CONFIGS["cfg2_chaos_mri"]
+    vol = synth.make_volume(99, Q=cfg["Q"], L=cfg["L"], C=cfg["C"], h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"])
+    eng.set_support(_t(vol.sup), _t(vol.fg))
+    q = _t(vol.qry)
+    hdr, recs = eng.run(q)
+    H, R = ops.decode_headers(hdr), ops.decode_records(recs)
+    assert len(H) == cfg["Q"] * cfg["L"] and not (H["flags"] & (_lib.IMG_RUN_OVERFLOW | _lib.IMG_CC_TRUNCATED)).any()
+    for i in range(len(H)):
+        r = R[i, : H["n_rec"][i]]
+        assert r["area"].sum() == H["n_fg"][i]                          # components partition the foreground
+        assert (r["box"][:, 0] <= r["conf_pt"][:, 0]).all() and (r["conf_pt"][:, 0] <= r["box"][:, 2]).all()
+        assert (r["box"][:, 1] <= r["conf_pt"][:, 1]).all() and (r["conf_pt"][:, 1] <= r["box"][:, 3]).all()
+        assert np.all(np.diff(r["label"]) == 1)
+    # determinism + slice-permutation equivariance (slices are independent given the prototypes)
+    hdr2, recs2 = eng.run(q)
+    assert torch.equal(hdr, hdr2) and torch.equal(recs, recs2)
+    perm = torch.randperm(cfg["Q"], generator=torch.Generator().manual_seed(0)).to(DEV)
+    hdr3, recs3 = eng.run(q[perm].contiguous())
+    Lb = cfg["L"]
+    idx = (perm[:, None] * Lb + torch.arange(Lb, device=DEV)[None]).reshape(-1)
+    assert torch.equal(hdr3, hdr[idx]) and torch.equal(recs3, recs[idx])
