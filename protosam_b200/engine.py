@@ -137,15 +137,21 @@ class CoarseVolumeEngine:
                                      algo=self.match_algo)
         return scores.view(Q * self.n_labels, 2, h, w)
 
-    def run(self, qry_feats: torch.Tensor):
-        """-> (hdr uint8 [Q*L,64], recs uint8 [Q*L,max_cc,96]) on the device; image index = q*L + l."""
-        logits = self.match(qry_feats)
+    def prompts_from_logits(self, logits: torch.Tensor):
+        """coarse logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on the device."""
         n = logits.shape[0]
         need = ops._lib.load().psam_coarse_to_prompts_workspace(n, self.out_size, self.max_runs, self.max_cc)
         if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=qry_feats.device)
+            self._ws = torch.empty(need, dtype=torch.uint8, device=logits.device)
         return ops.coarse_to_prompts(logits, self.img_size, self.out_size, self.use_cca, self.max_cc,
                                      self.max_runs, workspace=self._ws)
+
+    def run(self, qry_feats: torch.Tensor):
+        """-> (hdr, recs) on the device; image index = q*L + l."""
+        return self.prompts_from_logits(self.match(qry_feats))
+
+    def match_kernel_name(self) -> str:
+        return {0: "k_match_simt (auto)", 1: "k_match_simt", 2: "k_match_tc"}.get(self.match_algo, "?")
 
     def run_sharded(self, qry_local: torch.Tensor, q_total: int, dst: int = 0):
         """This rank's block of a Q-slice volume (see shard_range) -> gathered records on `dst`."""
