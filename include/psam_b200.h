@@ -163,17 +163,27 @@ typedef struct psam_image_hdr {
  * the reference's CPU run.  Outputs, each optional (NULL to skip) except maskbits:
  *   p_fg     [n_img,out,out] float  probability of class 1 (written at every pixel)
  *   maskbits [n_img,out,out/32] uint32, bit (x&31) of word (y, x>>5) = argmax == 1
- *   probs2   [n_img,2,out,out] float  full softmax (`output_p`), for function-level parity */
+ *   probs2   [n_img,2,out,out] float  full softmax (`output_p`), for function-level parity
+ *   wstat    [n_img,out,out/32] uint64 per-32-pixel-word statistics consumed by psam_components:
+ *            low word = sum over the word's foreground pixels of p_fg * 2^24 (exact integer),
+ *            high word = max of (p_fg * 2^24) << 5 | (31 - lane): best probability, leftmost pixel
+ * fg_only != 0 (engine path, needs p_fg, wstat and a workspace): 32x32-pixel blocks whose result is
+ * known exactly from the low-resolution cells they depend on (all background / all saturated) are not
+ * evaluated, p_fg is written at foreground pixels only, and exp/division run only where class 1 can
+ * win (probs2 must be NULL).  The mask, p_fg at foreground pixels and wstat are identical to fg_only=0. */
+size_t psam_upsample_workspace(int n_img, int out);
+
 int psam_upsample_softmax(const float* logits, int n_img, int h, int w, int mid, int out,
-                          float* p_fg, uint32_t* maskbits, float* probs2, psam_stream_t stream);
+                          float* p_fg, uint32_t* maskbits, float* probs2, uint64_t* wstat, int fg_only,
+                          void* workspace, size_t workspace_bytes, psam_stream_t stream);
 
 /* max_runs: capacity of the per-CTA run table (foreground row segments per image). */
 size_t psam_prompts_workspace(int n_img, int out, int max_runs, int max_cc);
 
-/* maskbits + p_fg -> headers and records.  use_cca != 0 keeps only the most confident
+/* maskbits + p_fg (+ optional wstat, NULL = derive everything from p_fg) -> headers and records.  use_cca != 0 keeps only the most confident
  * component (util/utils.py:496-541).  labels_out (optional) [n_img,out,out] int32 receives
  * the cv2-numbered label image (0/1 image of the kept component with use_cca). */
-int psam_components(const uint32_t* maskbits, const float* p_fg, int n_img, int out,
+int psam_components(const uint32_t* maskbits, const float* p_fg, const uint64_t* wstat, int n_img, int out,
                     int use_cca, int max_cc, int max_runs,
                     psam_image_hdr* hdr, psam_prompt_rec* recs, int32_t* labels_out,
                     void* workspace, size_t workspace_bytes, psam_stream_t stream);

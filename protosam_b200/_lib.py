@@ -39,9 +39,10 @@ SIGNATURES = {
     "psam_alp_match_workspace": (c_sz, [c_i] * 6),
     "psam_alp_match": (c_i, [c_p, c_i64, c_i64, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p,
                              c_p, c_sz, c_i, c_p]),
-    "psam_upsample_softmax": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "psam_upsample_workspace": (c_sz, [c_i, c_i]),
+    "psam_upsample_softmax": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_sz, c_p]),
     "psam_prompts_workspace": (c_sz, [c_i] * 4),
-    "psam_components": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "psam_components": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "psam_coarse_to_prompts_workspace": (c_sz, [c_i] * 4),
     "psam_coarse_to_prompts": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
 }

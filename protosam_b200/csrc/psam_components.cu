@@ -33,6 +33,7 @@ struct Acc {
 struct CompParams {
     const uint32_t* maskbits;
     const float* p_fg;
+    const uint2* wstat;      // per-word (sum, best) from kernel 3a, or NULL: read p_fg pixel by pixel
     int n_img, out, use_cca, max_cc, max_runs;
     psam_image_hdr* hdr;
     psam_prompt_rec* recs;
@@ -136,6 +137,45 @@ __device__ int topk1_small(TK* q, int n)
     return q[0].i;
 }
 
+// Exact statistics of one foreground run [s,e] of row y, computed by a whole warp:
+//   sum  = sum of p_fg * 2^24 over the run (integer, exact)
+//   best = max over the run of (p bits << 32 | ~raster index): highest p_fg, then first pixel.
+// A word whose foreground bits all belong to this run contributes through kernel 3a's per-word
+// statistics (8 bytes instead of 128); words shared with another run fall back to the pixels.
+__device__ __forceinline__ void run_stats(const uint32_t* __restrict__ bits, const float* __restrict__ pfg,
+                                          const uint2* __restrict__ wstat, int out, int wpr, int y, int s, int e,
+                                          int lane, unsigned long long& sum, unsigned long long& best)
+{
+    sum = 0; best = 0;
+    const int wa = s >> 5, wb = e >> 5;
+    for (int j = wa + lane; j <= wb; j += 32) {
+        const int lo = (j == wa) ? (s & 31) : 0, hi = (j == wb) ? (e & 31) : 31;
+        const uint32_t fm = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        const uint32_t m = bits[(size_t)y * wpr + j];
+        if (wstat && (m & ~fm) == 0u) {
+            const uint2 st = wstat[(size_t)y * wpr + j];
+            sum += st.x;
+            const uint32_t k = st.y >> 5, x = j * 32 + 31 - (st.y & 31);
+            // k = p * 2^24 in [2^23, 2^24]  ->  float bits of p
+            const uint32_t pb = (k == 16777216u) ? 0x3f800000u : (0x3f000000u + ((k - 8388608u)));
+            best = max(best, ((unsigned long long)pb << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * out + x)));
+        } else {
+            for (int b = lo; b <= hi; ++b) {
+                const int x = j * 32 + b;
+                const float pv = pfg[(size_t)y * out + x];
+                sum += (unsigned long long)(pv * 16777216.0f);
+                best = max(best, ((unsigned long long)__float_as_uint(pv) << 32) |
+                                     (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * out + x)));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += shfl_xor_u64(sum, o);
+        best = max(best, shfl_xor_u64(best, o));
+    }
+}
+
 __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
 {
     __shared__ int s_rowstart[MAX_OUT + 1];
@@ -162,6 +202,7 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
     for (int img = blockIdx.x; img < P.n_img; img += gridDim.x) {
         const uint32_t* bits = P.maskbits + (size_t)img * out * wpr;
         const float* pfg = P.p_fg + (size_t)img * out * out;
+        const uint2* wst = P.wstat ? P.wstat + (size_t)img * out * wpr : nullptr;
         psam_image_hdr* hdr = P.hdr + img;
         psam_prompt_rec* recs = P.recs + (size_t)img * P.max_cc;
         int32_t* labels = P.labels_out ? P.labels_out + (size_t)img * out * out : nullptr;
@@ -174,8 +215,18 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
         if (tid <= MAX_OUT) s_rowstart[tid] = 0;
         if (tid == 0) s_rowstart[MAX_OUT] = 0;
         __syncthreads();
-        for (int y = wid; y < out; y += CT / 32) {
-            const uint32_t word = lane < wpr ? bits[(size_t)y * wpr + lane] : 0u;
+        for (int yb = wid; yb < out; yb += 4 * (CT / 32)) {
+          uint32_t wq[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {     // four independent row loads in flight per warp
+              const int y = yb + u * (CT / 32);
+              wq[u] = (lane < wpr && y < out) ? bits[(size_t)y * wpr + lane] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int y = yb + u * (CT / 32);
+            if (y >= out) break;
+            const uint32_t word = wq[u];
             uint32_t prev_msb = __shfl_up_sync(0xffffffffu, word >> 31, 1);
             if (lane == 0) prev_msb = 0;
             const uint32_t starts = word & ~((word << 1) | prev_msb);
@@ -194,6 +245,7 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
                 }
             }
             if (lane == 0) s_rowstart[y] = tot;
+          }
         }
         // block reductions of the S1 scalars
         npix = warp_sum_i(npix);
@@ -296,30 +348,53 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
         for (int i = tid; i < key_words; i += CT) s_bitmap[i] = 0u;
         __syncthreads();
 
-        // ---- S4: union runs of adjacent rows that touch (8-connectivity) -------------------
+        // ---- S4: connect runs of adjacent rows that touch (8-connectivity) ----------------------
+        // A blob is a chain of ~1000 vertically stacked runs, so plain union-find degenerates into
+        // O(rows) pointer chasing per run.  Instead: (a) link every run to its FIRST neighbour in the
+        // row above (a forest, no atomics), (b) pointer-jump until flat (log2(depth) rounds), (c) merge
+        // the trees joined by the remaining neighbours with lock-free unions on now-shallow trees,
+        // (d) pointer-jump again.
         for (int i = tid; i < total; i += CT) {
             const int y = run_y[i];
-            if (y == 0) continue;
-            const int s = run_s[i], e = run_e[i];
-            int lo = s_rowstart[y - 1];
-            const int hi = s_rowstart[y];
-            int l = lo, r = hi;   // first j with run_e[j] >= s - 1
-            while (l < r) {
-                const int m = (l + r) >> 1;
-                if ((int)run_e[m] < s - 1) l = m + 1; else r = m;
+            int link = i;
+            if (y > 0) {
+                const int s = run_s[i], e = run_e[i];
+                int l = s_rowstart[y - 1], r = s_rowstart[y];
+                const int hi = r;           // first j with run_e[j] >= s - 1
+                while (l < r) {
+                    const int m = (l + r) >> 1;
+                    if ((int)run_e[m] < s - 1) l = m + 1; else r = m;
+                }
+                if (l < hi && (int)run_s[l] <= e + 1) link = l;
+                rank[i] = l;                // remembered for (c)
             }
-            for (int j = l; j < hi && (int)run_s[j] <= e + 1; ++j) uf_union(parent, i, j);
+            parent[i] = link;
         }
         __syncthreads();
-        // ---- S5/S6: flatten; first 2x2 block (block-raster order) of every component -------
+        for (int pass = 0; pass < 2; ++pass) {
+            for (;;) {                      // (b)/(d) pointer jumping
+                int changed = 0;
+                for (int i = tid; i < total; i += CT) {
+                    const int pp = ((volatile int32_t*)parent)[i];
+                    const int gp = ((volatile int32_t*)parent)[pp];
+                    if (gp != pp) { parent[i] = gp; changed = 1; }
+                }
+                if (!__syncthreads_or(changed)) break;
+            }
+            if (pass == 1) break;
+            for (int i = tid; i < total; i += CT) {   // (c) remaining neighbours
+                const int y = run_y[i];
+                if (y == 0) continue;
+                const int e = run_e[i], hi = s_rowstart[y];
+                for (int j = rank[i] + 1; j < hi && (int)run_s[j] <= e + 1; ++j) uf_union(parent, i, j);
+            }
+            __syncthreads();
+        }
+        // ---- S5/S6: first 2x2 block (block-raster order) of every component -------------------
         for (int i = tid; i < total; i += CT) {
-            const int r = uf_find(parent, i);
             const uint32_t key = (uint32_t)(run_y[i] >> 1) * bw + (run_s[i] >> 1);
-            atomicMin(&minkey[r], key);
-            rank[i] = r;   // stash the root; parent[] stays a valid forest for concurrent finds
+            atomicMin(&minkey[parent[i]], key);
         }
-        __syncthreads();
-        for (int i = tid; i < total; i += CT) parent[i] = rank[i];
         __syncthreads();
         // ---- S7-S9: OpenCV label = 1 + rank of that block among all components' first blocks
         for (int i = tid; i < total; i += CT)
@@ -358,12 +433,8 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
         int sel_root = -1, flags = 0;
         if (P.use_cca) {
             for (int i = wid; i < total; i += CT / 32) {
-                const int y = run_y[i], s = run_s[i], e = run_e[i];
-                unsigned long long acc_p = 0;
-                for (int x = s + lane; x <= e; x += 32)
-                    acc_p += (unsigned long long)(pfg[(size_t)y * out + x] * 16777216.0f);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc_p += shfl_xor_u64(acc_p, o);
+                unsigned long long acc_p, b_unused;
+                run_stats(bits, pfg, wst, out, wpr, run_y[i], run_s[i], run_e[i], lane, acc_p, b_unused);
                 if (lane == 0) atomicAdd(&sump[parent[i]], acc_p);
             }
             __syncthreads();
@@ -416,19 +487,8 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
             const int slot = P.use_cca ? (root == sel_root ? 0 : -1) : (rank[root] < P.max_cc ? rank[root] : -1);
             if (slot < 0) continue;
             const int y = run_y[i], s = run_s[i], e = run_e[i];
-            unsigned long long acc_p = 0, best = 0;
-            for (int x = s + lane; x <= e; x += 32) {
-                const float pv = pfg[(size_t)y * out + x];
-                acc_p += (unsigned long long)(pv * 16777216.0f);
-                const unsigned long long k = ((unsigned long long)__float_as_uint(pv) << 32) |
-                                             (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * out + x));
-                best = max(best, k);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                acc_p += shfl_xor_u64(acc_p, o);
-                best = max(best, shfl_xor_u64(best, o));
-            }
+            unsigned long long acc_p, best;
+            run_stats(bits, pfg, wst, out, wpr, y, s, e, lane, acc_p, best);
             if (lane == 0) {
                 Acc* a = acc + slot;
                 const unsigned int len = e - s + 1;
@@ -526,7 +586,7 @@ extern "C" size_t psam_prompts_workspace(int n_img, int out, int max_runs, int m
     return comp_scratch_bytes(comp_grid(n_img), max_runs, max_cc);
 }
 
-extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, int n_img, int out, int use_cca,
+extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, const uint64_t* wstat, int n_img, int out, int use_cca,
                                int max_cc, int max_runs, psam_image_hdr* hdr, psam_prompt_rec* recs,
                                int32_t* labels_out, void* workspace, size_t workspace_bytes, psam_stream_t stream_)
 {
@@ -542,7 +602,7 @@ extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, int 
         return PSAM_ERR_WORKSPACE;
     }
     CompParams P;
-    P.maskbits = maskbits; P.p_fg = p_fg; P.n_img = n_img; P.out = out; P.use_cca = use_cca ? 1 : 0;
+    P.maskbits = maskbits; P.p_fg = p_fg; P.wstat = reinterpret_cast<const uint2*>(wstat); P.n_img = n_img; P.out = out; P.use_cca = use_cca ? 1 : 0;
     P.max_cc = max_cc; P.max_runs = max_runs; P.hdr = hdr; P.recs = recs; P.labels_out = labels_out;
     Carver cv(workspace);
     const size_t n = (size_t)ctas * max_runs;
@@ -576,6 +636,8 @@ extern "C" size_t psam_coarse_to_prompts_workspace(int n_img, int out, int max_r
     size_t b = 0;
     b += align_up(sizeof(float) * (size_t)n_img * out * out, 256);            // p_fg
     b += align_up(sizeof(uint32_t) * (size_t)n_img * out * (out / 32), 256);  // mask bits
+    b += align_up(sizeof(uint2) * (size_t)n_img * out * (out / 32), 256);     // per-word statistics
+    b += align_up(psam_upsample_workspace(n_img, out), 256);                  // block work list
     b += psam_prompts_workspace(n_img, out, max_runs, max_cc);
     return b + 256;
 }
@@ -592,9 +654,12 @@ extern "C" int psam_coarse_to_prompts(const float* logits, int n_img, int h, int
     Carver cv(workspace);
     float* p_fg = cv.take<float>((size_t)n_img * out * out);
     uint32_t* bits = cv.take<uint32_t>((size_t)n_img * out * (out / 32));
+    uint64_t* wstat = cv.take<uint64_t>((size_t)n_img * out * (out / 32));
+    const size_t upw = psam_upsample_workspace(n_img, out);
+    char* upws = cv.take<char>(upw);
     char* rest = static_cast<char*>(workspace) + cv.used();
-    int rc = psam_upsample_softmax(logits, n_img, h, w, mid, out, p_fg, bits, nullptr, stream);
+    int rc = psam_upsample_softmax(logits, n_img, h, w, mid, out, p_fg, bits, nullptr, wstat, 1, upws, upw, stream);
     if (rc) return rc;
-    return psam_components(bits, p_fg, n_img, out, use_cca, max_cc, max_runs, hdr, recs, nullptr, rest,
+    return psam_components(bits, p_fg, wstat, n_img, out, use_cca, max_cc, max_runs, hdr, recs, nullptr, rest,
                            workspace_bytes - cv.used(), stream);
 }

@@ -123,8 +123,9 @@ def alp_match(qry, protos, want_assign=True, want_sims=False, algo=0):
 
 # ------------------------------------------------------------------ kernel 3
 
-def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False):
-    """logits [n,2,h,w] -> (p_fg [n,out,out] | None, maskbits [n,out,out//32] int32, probs2 | None)."""
+def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False, fg_only=False, want_wstat=False):
+    """logits [n,2,h,w] -> (p_fg [n,out,out] | None, maskbits [n,out,out//32] int32, probs2 | None
+    [, wstat int64 [n,out,out//32]]).  fg_only: the engine's variant (p_fg valid at foreground pixels only)."""
     L = _lib.load()
     _need_cuda(logits)
     logits = logits.contiguous()
@@ -134,13 +135,20 @@ def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False):
     p_fg = torch.empty((n, out, out), dtype=torch.float32, device=dev) if want_p_fg else None
     bits = torch.empty((n, out, out // 32), dtype=torch.int32, device=dev)
     probs2 = torch.empty((n, 2, out, out), dtype=torch.float32, device=dev) if want_probs2 else None
+    wstat = torch.zeros((n, out, out // 32), dtype=torch.int64, device=dev) if want_wstat else None
+    if fg_only and p_fg is not None:
+        p_fg.zero_()
+    ws = _ws(L.psam_upsample_workspace(n, int(out)), dev)
     rc = L.psam_upsample_softmax(_ptr(logits), n, h, w, int(mid), int(out), _ptr(p_fg), _ptr(bits), _ptr(probs2),
-                                 _stream())
+                                 _ptr(wstat), int(bool(fg_only)), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "psam_upsample_softmax")
+    if want_wstat:
+        return p_fg, bits, probs2, wstat
     return p_fg, bits, probs2
 
 
-def components(maskbits, p_fg, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DEFAULT_MAX_RUNS, want_labels=False):
+def components(maskbits, p_fg, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DEFAULT_MAX_RUNS, want_labels=False,
+               wstat=None):
     """-> (hdr uint8 [n,64], recs uint8 [n,max_cc,96], labels int32 [n,out,out] | None), all on device."""
     L = _lib.load()
     _need_cuda(p_fg)
@@ -150,7 +158,7 @@ def components(maskbits, p_fg, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DE
     recs = torch.zeros((n, max_cc, REC_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     labels = torch.empty((n, out, out), dtype=torch.int32, device=dev) if want_labels else None
     ws = _ws(L.psam_prompts_workspace(n, out, max_runs, max_cc), dev)
-    rc = L.psam_components(_ptr(maskbits), _ptr(p_fg), n, out, int(bool(use_cca)), max_cc, max_runs, _ptr(hdr),
+    rc = L.psam_components(_ptr(maskbits), _ptr(p_fg), _ptr(wstat), n, out, int(bool(use_cca)), max_cc, max_runs, _ptr(hdr),
                            _ptr(recs), _ptr(labels), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "psam_components")
     return hdr, recs, labels

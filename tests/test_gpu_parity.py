@@ -325,3 +325,19 @@ def test_full_size_properties_cfg2():
     Lb = cfg["L"]
     idx = (perm[:, None] * Lb + torch.arange(Lb, device=DEV)[None]).reshape(-1)
     assert torch.equal(hdr3, hdr[idx]) and torch.equal(recs3, recs[idx])
+
+
+@pytest.mark.parametrize("h,S", [(37, 518), (73, 1024), (48, 672)])
+def test_engine_variant_of_upsample_equals_full_variant(h, S):
+    """fg-only evaluation + per-word statistics give the same mask, probabilities and records as
+    the every-pixel variant followed by pixel-wise statistics."""
+    low = np.concatenate([(synth.gaussian_like(h + S, (2, 2, h, h)) * 9), synth.gaussian_like(5, (1, 2, h, h)) * 1e-4]).astype(np.float32)
+    p_full, bits_full, _ = ops.upsample_softmax(_t(low), S, 1024)
+    p_fg, bits, _, wstat = ops.upsample_softmax(_t(low), S, 1024, fg_only=True, want_wstat=True)
+    assert torch.equal(bits, bits_full)
+    mask = torch.from_numpy(np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little").reshape(3, 1024, 1024)).bool().to(DEV)
+    assert torch.equal(p_fg[mask], p_full[mask])
+    for use_cca in (False, True):
+        a = ops.components(bits, p_fg, use_cca=use_cca, max_cc=4096, wstat=wstat)
+        b = ops.components(bits_full, p_full, use_cca=use_cca, max_cc=4096)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
