@@ -20,26 +20,11 @@
 // in fp32 and no rescaling pass is needed.
 #include <math_constants.h>
 
-#include "psam_common.cuh"
+#include "psam_match.cuh"
 
 namespace psam {
 
 constexpr int BM = 128, BN = 64, BK = 16, APAD = 4;
-
-struct MatchParams {
-    const float* qry;
-    int64_t slice_stride, row_stride;
-    int Q, HW, C;
-    const float* protos;
-    int cap_rows;
-    const int32_t* counts;
-    const int32_t* eff_modes;
-    int nsets;
-    float* scores;
-    float* assign;
-    float* sims;
-    int32_t* status;
-};
 
 __global__ void __launch_bounds__(256) k_match_simt(MatchParams p)
 {
@@ -211,8 +196,10 @@ using namespace psam;
 
 extern "C" size_t psam_alp_match_workspace(int Q, int HW, int C, int nsets, int cap_rows, int algo)
 {
-    (void)Q; (void)HW; (void)C; (void)nsets; (void)cap_rows; (void)algo;
-    return 256;
+    // algo 1 needs no scratch; 0 (auto) and 2 may run the tensor-core variant, which stages bf16 operand images
+    if (algo == 1 || Q < 1 || HW < 1 || C < 1 || nsets < 1 || cap_rows < 1) return 256;
+    if (!match_tc_supported(Q, HW, C, nsets, cap_rows, false)) return 256;
+    return match_tc_workspace(Q, HW, C, nsets, cap_rows);
 }
 
 extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t row_stride, int Q, int HW, int C,
@@ -220,7 +207,6 @@ extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t ro
                               int nsets, float* scores, float* assign, float* sims, int32_t* status, void* workspace,
                               size_t workspace_bytes, int algo, psam_stream_t stream_)
 {
-    (void)workspace; (void)workspace_bytes;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(qry && protos && counts && eff_modes && scores && status, "psam_alp_match: null pointer");
     PSAM_CHECK_ARG(Q >= 1 && Q <= 65535 && HW >= 1 && C >= 1 && nsets >= 1 && nsets <= 65535 && cap_rows >= 1,
@@ -230,11 +216,13 @@ extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t ro
     PSAM_CHECK_ARG((reinterpret_cast<uintptr_t>(qry) & 15) == 0 && (reinterpret_cast<uintptr_t>(protos) & 15) == 0,
                    "psam_alp_match: qry/protos must be 16-byte aligned");
     PSAM_CHECK_ARG(algo >= 0 && algo <= 2, "psam_alp_match: algo %d", algo);
-    if (algo == 2) {
-        set_error("psam_alp_match: tensor-core variant not built in this revision");
-        return PSAM_ERR_UNSUPPORTED;
-    }
     MatchParams p{qry, slice_stride, row_stride, Q, HW, C, protos, cap_rows, counts, eff_modes,
                   nsets, scores, assign, sims, status};
+    if (algo == 2) return launch_match_tc(p, workspace, workspace_bytes, stream);
+    // auto: tensor cores whenever the variant applies (the raw-similarity dump for visualisation and channel
+    // counts that are not a multiple of 8 stay on the CUDA-core kernel) and the caller sized the workspace for it
+    if (algo == 0 && match_tc_supported(Q, HW, C, nsets, cap_rows, sims != nullptr) && workspace &&
+        workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows))
+        return launch_match_tc(p, workspace, workspace_bytes, stream);
     return launch_match_simt(p, stream);
 }

@@ -1,0 +1,552 @@
+// Kernel 2 (tensor-core variant) -- fused query x prototype match on tcgen05 (sm_100a).
+//
+// Replaces safe_norm(qry) + get_prediction_from_prototypes of the reference
+// (models/alpmodule.py:14-18, 57-94, 195).  Same contract as the CUDA-core variant
+// (psam_match_simt.cu): d[m,n] = 20 * <q_m, p_n> / max(|q_m|, 1e-4) against the already
+// normalised prototypes, reduced over the prototype axis of each set in the epilogue
+// (softmax-weighted sum + argmax for the grid modes, max for 'mask'), so the [P, HW] similarity
+// tensor never exists in memory.
+//
+// Why tensor cores: ncu on the CUDA-core variant (profiles/r1_prof_match_simt_raw.csv) shows the
+// [HW x C].[C x sum(P)] contraction compute-bound on the FMA pipe at the named shapes (DRAM 0.6 %
+// of peak, arithmetic intensity sum(P)/2 = 600 FLOP/B at config 2).
+//
+// Why three bf16 passes instead of one TF32 pass: maps must stay within 1e-3 absolute of the fp32
+// reference.  A TF32 operand keeps 10 mantissa bits; on unit vectors of C = 768 that is a
+// ~3e-4 (1 sigma) error on d = 20*cos, too thin over millions of outputs.  Each fp32 operand is
+// therefore split x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and the product is evaluated
+// as  hi_a*hi_b + lo_a*hi_b + hi_a*lo_b  (kind::f16, fp32 accumulation in TMEM); the dropped
+// lo_a*lo_b term and the rounding of lo are both ~2^-17 relative, i.e. the result is fp32-grade
+// (measured max |d - d_fp32| ~ 1e-5) at 1.5x the tensor time of a single TF32 pass.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   k_pack_query   fp32 query rows -> per (128-row tile, 64-channel block) operand images: bf16
+//                  hi/lo planes already in the 128-byte-swizzled K-major layout the MMA reads,
+//                  plus the per-row scale 20/max(|q|,1e-4).  [round-1 layout; fusing this pass into
+//                  the GEMM producer is the next step, see DESIGN.md]
+//   k_pack_protos  the same for the prototype rows of all sets, concatenated (each set padded to
+//                  16 columns) so one B matrix serves every set.
+//   k_match_tc     warp 0: one thread streams operand blocks global -> shared with cp.async.bulk
+//                  (TMA engine, mbarrier complete_tx) through a 2-stage ring;
+//                  warp 1: one thread issues tcgen05.mma (M=128, N<=256, K=16, 12 per k-block)
+//                  into one of two 256-column TMEM accumulators and commits to mbarriers;
+//                  warps 2-5: epilogue -- tcgen05.ld 16 columns at a time, scale, exp2, running
+//                  sum(e), sum(e*d), max/argmax per set, store one float per (row, set).
+//                  MMA of chunk i+1 overlaps the epilogue of chunk i.
+//
+// Roofline: tensor-bound.  Algorithmic flops per (slice, set) = 2*HW*C*P (executed: 3x that in
+// bf16).  Algorithmic bytes: SURVEY.md section 8(d).
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "psam_match.cuh"
+
+namespace psam {
+
+namespace tc {
+
+constexpr int BM = 128;                          // query rows per tile = TMEM lanes
+constexpr int BK = 64;                           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int NCH = 256;                         // prototype columns per TMEM accumulator buffer
+constexpr int STAGES = 2;
+constexpr int GROUP_BYTES = 2048;                // 8 rows x 128 B: hi plane (1024 B) then lo plane (1024 B)
+constexpr int A_STAGE_BYTES = BM / 8 * GROUP_BYTES;    // 32 KB
+constexpr int B_STAGE_BYTES = NCH / 8 * GROUP_BYTES;   // 64 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for the 1024-byte alignment
+constexpr int MAX_SETS = 128;
+constexpr int MAX_SPLIT = 8;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__host__ __device__ __forceinline__ int pad16(int x) { return (x + 15) & ~15; }
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared bulk copy on the TMA engine, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128, N from idesc, K=16
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand, 128-byte swizzle, 8-row groups GROUP_BYTES apart (cute::UMMA::SmemDescriptor:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(GROUP_BYTES >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+// cute::UMMA::InstrDescriptor: D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ------------------------------------------------------------------------------ operand packing
+// 8 fp32 -> 8 bf16 hi + 8 bf16 lo (x = hi + lo up to 2^-17 relative)
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(hb);
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+        l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// One warp per operand row: reads the row's channels 8 at a time (1 KB per warp iteration, coalesced),
+// writes 16-byte chunks of the hi and lo planes at their swizzled position inside the row's 8-row group
+// (chunk c of row r lands at r*128 + ((c ^ r) << 4)), returns the row's sum of squares.
+__device__ __forceinline__ float pack_row(const float* __restrict__ src, bool valid, int C, int KB, int lane,
+                                          uint8_t* __restrict__ group0, size_t kb_stride, int r)
+{
+    float ssq = 0.f;
+    for (int ch = lane; ch < KB * 8; ch += 32) {
+        const int k0 = ch * 8;
+        float v[8];
+        if (valid && k0 < C) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(src + k0));
+            const float4 y = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ssq = fmaf(v[i], v[i], ssq);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        const int kb = ch >> 3, c = ch & 7;
+        uint8_t* dst = group0 + (size_t)kb * kb_stride + r * 128 + ((c ^ r) << 4);
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + 1024) = lo;
+    }
+    return warp_sum(ssq);
+}
+
+// a_img[tile][kb][16 groups][2048 B]; rows beyond R are zero-filled.  grid = ntiles*128/8 blocks of 256.
+__global__ void __launch_bounds__(256) k_pack_query(const float* __restrict__ qry, int64_t slice_stride,
+                                                    int64_t row_stride, int HW, int R, int C, int KB,
+                                                    uint8_t* __restrict__ a_img, float* __restrict__ scale)
+{
+    const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int tile = g >> 7, grp = (g & 127) >> 3, r = g & 7;
+    const bool valid = g < R;
+    const float* src = valid ? qry + (size_t)(g / HW) * slice_stride + (size_t)(g % HW) * row_stride : qry;
+    uint8_t* group0 = a_img + ((size_t)tile * KB * 16 + grp) * GROUP_BYTES;
+    const float ssq = pack_row(src, valid, C, KB, lane, group0, (size_t)16 * GROUP_BYTES, r);
+    if (lane == 0) scale[g] = valid ? 20.0f / fmaxf(sqrtf(ssq), 1e-4f) : 0.f;
+}
+
+// b_img[kb][G groups][2048 B] over the concatenated, 16-padded prototype columns of all sets.
+// grid = (ceil(pad16(cap_rows)/8), nsets), block = 256 (one warp per row of the group).
+__global__ void __launch_bounds__(256) k_pack_protos(const float* __restrict__ protos, int cap_rows,
+                                                     const int32_t* __restrict__ counts, int C, int KB, int G,
+                                                     uint8_t* __restrict__ b_img)
+{
+    __shared__ int s_base;
+    const int set = blockIdx.y, count = counts[set];
+    const int row0 = blockIdx.x * 8;
+    if (row0 >= pad16(count)) return;
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int s = 0; s < set; ++s) b += pad16(counts[s]);
+        s_base = b;
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = row0 + wid, col = s_base + n;
+    const bool valid = n < count;
+    const float* src = protos + ((size_t)set * cap_rows + (valid ? n : 0)) * C;
+    uint8_t* group0 = b_img + (size_t)(col >> 3) * GROUP_BYTES;
+    pack_row(src, valid, C, KB, lane, group0, (size_t)G * GROUP_BYTES, col & 7);
+}
+
+// ------------------------------------------------------------------------------ the GEMM + reduction
+struct TcParams {
+    const uint8_t* a_img;
+    const uint8_t* b_img;
+    const float* scale;
+    const int32_t* counts;
+    const int32_t* eff_modes;
+    float* scores;
+    float* assign;
+    int32_t* status;
+    int nsets, HW, R, ntiles, KB, G, nsplit;
+};
+
+struct RowAcc {
+    float se, sed, best;
+    int bi;
+};
+
+template <bool kFull>
+__device__ __forceinline__ void fold16(const float (&v)[16], int nvalid, int nbase, float sc, float sc2, RowAcc& a)
+{
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (kFull || j < nvalid) {
+            const float x = v[j];
+            const float e = ex2(fmaf(x, sc2, -20.0f * LOG2E));   // exp(d - 20), d = x*sc in [-20, 20]
+            a.se += e;
+            a.sed = fmaf(e, x * sc, a.sed);
+            if (x > a.best) { a.best = x; a.bi = nbase + j; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_count[MAX_SETS];
+    __shared__ int s_split_set[MAX_SPLIT + 1], s_split_col[MAX_SPLIT + 1];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    if (threadIdx.x == 0) {
+        int T = 0;
+        for (int s = 0; s < p.nsets; ++s) {
+            const int c = p.counts[s];
+            s_count[s] = c;
+            T += pad16(c);
+        }
+        // column splits at set boundaries, as even as the set sizes allow
+        s_split_set[0] = 0;
+        s_split_col[0] = 0;
+        int acc = 0, k = 1;
+        for (int s = 0; s < p.nsets && k < p.nsplit; ++s) {
+            acc += pad16(s_count[s]);
+            while (k < p.nsplit && (long long)acc * p.nsplit >= (long long)k * T) {
+                s_split_set[k] = s + 1;
+                s_split_col[k] = acc;
+                ++k;
+            }
+        }
+        for (; k < p.nsplit; ++k) { s_split_set[k] = p.nsets; s_split_col[k] = T; }
+        s_split_set[p.nsplit] = p.nsets;
+        s_split_col[p.nsplit] = T;
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_tfull[i], 1); mbar_init(&s_tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int nitems = p.ntiles * p.nsplit;
+
+    if (warp == 0) {
+        // ===== producer: operand blocks global -> shared =====
+        if (lane == 0) {
+            uint32_t kit = 0;
+            for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+                const int split = it / p.ntiles, tile = it - split * p.ntiles;
+                const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
+                const uint8_t* a_tile = p.a_img + (size_t)tile * p.KB * A_STAGE_BYTES;
+                for (int n0 = c0; n0 < c1; n0 += NCH) {
+                    const uint32_t bytes_b = (uint32_t)min(NCH, c1 - n0) * (GROUP_BYTES / 8);
+                    for (int kb = 0; kb < p.KB; ++kb, ++kit) {
+                        const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                        mbar_wait(&s_empty[s], ph ^ 1);
+                        uint8_t* sa = smem + s * STAGE_BYTES;
+                        mbar_expect_tx(&s_full[s], A_STAGE_BYTES + bytes_b);
+                        bulk_g2s(sa, a_tile + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &s_full[s]);
+                        bulk_g2s(sa + A_STAGE_BYTES, p.b_img + ((size_t)kb * p.G + (n0 >> 3)) * GROUP_BYTES, bytes_b,
+                                 &s_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t kit = 0, cit = 0;
+            for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+                const int split = it / p.ntiles;
+                const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
+                for (int n0 = c0; n0 < c1; n0 += NCH, ++cit) {
+                    const uint32_t b = cit & 1, tph = (cit >> 1) & 1;
+                    mbar_wait(&s_tempty[b], tph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + b * NCH;
+                    const uint32_t idesc = make_idesc(min(NCH, c1 - n0));
+                    for (int kb = 0; kb < p.KB; ++kb, ++kit) {
+                        const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                        mbar_wait(&s_full[s], ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t a_hi = make_sdesc(a_addr + k * 32), a_lo = make_sdesc(a_addr + 1024 + k * 32);
+                            const uint64_t b_hi = make_sdesc(b_addr + k * 32), b_lo = make_sdesc(b_addr + 1024 + k * 32);
+                            tc_mma(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);
+                            tc_mma(d_tmem, a_lo, b_hi, idesc, 1);
+                            tc_mma(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
+                        tc_commit(&s_empty[s]);        // frees the smem stage when these MMAs retire
+                    }
+                    tc_commit(&s_tfull[b]);            // accumulator complete
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> per-set reductions -> global =====
+        const int lg = warp & 3;                       // TMEM lane group this warp may read
+        const int row_in_tile = lg * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        uint32_t cit = 0;
+        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+            const int split = it / p.ntiles, tile = it - split * p.ntiles;
+            const int c0 = s_split_col[split];
+            const int g = tile * BM + row_in_tile;
+            const bool valid = g < p.R;
+            const int q = valid ? g / p.HW : 0, pix = valid ? g - q * p.HW : 0;
+            const float sc = valid ? __ldg(p.scale + g) : 0.f;
+            const float sc2 = sc * LOG2E;
+            int col = 0;                                // column cursor relative to c0
+            int cur_chunk = -1;
+            uint32_t b = 0;
+            for (int set = s_split_set[split]; set < s_split_set[split + 1]; ++set) {
+                const int cnt = s_count[set];
+                const size_t o = ((size_t)q * p.nsets + set) * p.HW + pix;
+                if (cnt <= 0) {   // empty grid set: the reference raises (alpmodule.py:68); report, write NaN
+                    if (valid) {
+                        p.scores[o] = CUDART_NAN_F;
+                        if (p.assign) p.assign[o] = CUDART_NAN_F;
+                    }
+                    if (g == 0) atomicOr(p.status + set, PSAM_SET_EMPTY);
+                    continue;
+                }
+                RowAcc a{0.f, 0.f, -CUDART_INF_F, 0};
+                for (int nb = 0; nb < cnt; nb += 16, col += 16) {
+                    const int chunk = col / NCH;
+                    if (chunk != cur_chunk) {
+                        if (cur_chunk >= 0) {           // done with the previous accumulator buffer
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&s_tempty[b]);
+                            ++cit;
+                        }
+                        b = cit & 1;
+                        mbar_wait(&s_tfull[b], (cit >> 1) & 1);
+                        tc_fence_after();
+                        cur_chunk = chunk;
+                    }
+                    float v[16];
+                    tc_ld16(lane_addr + b * NCH + (col - chunk * NCH), v);
+                    const int nvalid = cnt - nb;
+                    if (nvalid >= 16) fold16<true>(v, 16, nb, sc, sc2, a);
+                    else fold16<false>(v, nvalid, nb, sc, sc2, a);
+                }
+                if (valid) {
+                    if (p.eff_modes[set] == PSAM_MODE_MASK) {
+                        const float d = a.best * sc;
+                        p.scores[o] = d;
+                        if (p.assign) p.assign[o] = d;
+                    } else {
+                        p.scores[o] = a.sed / a.se;
+                        if (p.assign) p.assign[o] = (float)a.bi;
+                    }
+                }
+            }
+            if (cur_chunk >= 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_tempty[b]);
+                ++cit;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+static int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+struct Layout {
+    int R, ntiles, KB, G;
+    size_t a_bytes, b_bytes, scale_bytes;
+};
+
+static Layout make_layout(int Q, int HW, int C, int nsets, int cap_rows)
+{
+    Layout L;
+    L.R = Q * HW;
+    L.ntiles = (L.R + BM - 1) / BM;
+    L.KB = (C + BK - 1) / BK;
+    L.G = nsets * pad16(cap_rows) / 8;
+    L.a_bytes = (size_t)L.ntiles * L.KB * A_STAGE_BYTES;
+    L.b_bytes = (size_t)L.KB * L.G * GROUP_BYTES;
+    L.scale_bytes = (size_t)L.ntiles * BM * sizeof(float);
+    return L;
+}
+
+}  // namespace tc
+
+bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want_sims)
+{
+    (void)cap_rows;
+    return !want_sims && C % 8 == 0 && nsets <= tc::MAX_SETS && (long long)Q * HW < (1ll << 30);
+}
+
+size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows)
+{
+    const tc::Layout L = tc::make_layout(Q, HW, C, nsets, cap_rows);
+    return align_up(L.a_bytes, 1024) + align_up(L.b_bytes, 1024) + align_up(L.scale_bytes, 1024) + 1024;
+}
+
+int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+    using namespace tc;
+    if (!match_tc_supported(p.Q, p.HW, p.C, p.nsets, p.cap_rows, p.sims != nullptr)) {
+        set_error("psam_alp_match: the tensor-core variant needs C %% 8 == 0, nsets <= %d and sims == NULL", MAX_SETS);
+        return PSAM_ERR_UNSUPPORTED;
+    }
+    if (!workspace || workspace_bytes < match_tc_workspace(p.Q, p.HW, p.C, p.nsets, p.cap_rows)) {
+        set_error("psam_alp_match: workspace too small for the tensor-core variant (%zu < %zu)", workspace_bytes,
+                  match_tc_workspace(p.Q, p.HW, p.C, p.nsets, p.cap_rows));
+        return PSAM_ERR_WORKSPACE;
+    }
+    const Layout L = make_layout(p.Q, p.HW, p.C, p.nsets, p.cap_rows);
+    uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+    uint8_t* a_img = base;
+    uint8_t* b_img = a_img + align_up(L.a_bytes, 1024);
+    float* scale = reinterpret_cast<float*>(b_img + align_up(L.b_bytes, 1024));
+
+    k_pack_protos<<<dim3(pad16(p.cap_rows) / 8, p.nsets), 256, 0, stream>>>(p.protos, p.cap_rows, p.counts, p.C, L.KB, L.G,
+                                                                           b_img);
+    PSAM_CHECK_LAUNCH("k_pack_protos");
+    k_pack_query<<<L.ntiles * BM / 8, 256, 0, stream>>>(p.qry, p.slice_stride, p.row_stride, p.HW, L.R, p.C, L.KB, a_img,
+                                                       scale);
+    PSAM_CHECK_LAUNCH("k_pack_query");
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("k_match_tc: cudaFuncSetAttribute(%d bytes): %s", SMEM_BYTES, cudaGetErrorString(e));
+            return PSAM_ERR_LAUNCH;
+        }
+        attr_set = true;
+    }
+    const int sms = sm_count();
+    int nsplit = (4 * sms + L.ntiles - 1) / L.ntiles;
+    nsplit = max(1, min(min(nsplit, p.nsets), MAX_SPLIT));
+    TcParams t{a_img, b_img, scale, p.counts, p.eff_modes, p.scores, p.assign, p.status,
+               p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit};
+    const int grid = min(sms, L.ntiles * nsplit);
+    k_match_tc<<<grid, THREADS, SMEM_BYTES, stream>>>(t);
+    PSAM_CHECK_LAUNCH("k_match_tc");
+    return PSAM_OK;
+}
+
+}  // namespace psam

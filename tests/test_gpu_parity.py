@@ -341,3 +341,73 @@ def test_engine_variant_of_upsample_equals_full_variant(h, S):
         a = ops.components(bits, p_fg, use_cca=use_cca, max_cc=4096, wstat=wstat)
         b = ops.components(bits_full, p_full, use_cca=use_cca, max_cc=4096)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ------------------------------------------------------------------------------ tensor-core match
+
+def _fake_protos(rng, counts, modes, cap, C):
+    """a prototype table as psam_alp_prototypes would write it: unit rows, arbitrary per-set counts"""
+    nsets = len(counts)
+    pr = rng.standard_normal((nsets, cap, C)).astype(np.float32)
+    pr /= np.linalg.norm(pr, axis=-1, keepdims=True)
+    return dict(protos=_t(pr), counts=_t(np.array(counts, np.int32)), cap_rows=cap,
+                eff_modes=_t(np.array([_lib.MODE_IDS[m] for m in modes], np.int32)),
+                status=torch.zeros(nsets, dtype=torch.int32, device=DEV))
+
+
+@pytest.mark.parametrize("Q,HW,C,counts,modes", [
+    (1, 128, 64, [16], ["gridconv"]),                                            # one tile, one k-block, one group
+    (1, 100, 64, [5], ["gridconv+"]),                                            # partial tile, partial group
+    (2, 1369, 768, [300, 9, 287, 1, 310, 33, 256, 17], ["gridconv", "gridconv+", "gridconv", "mask"] * 2),
+    (3, 1024, 384, [255, 1], ["gridconv", "mask"]),
+    (1, 2304, 1024, [577, 40], ["gridconv", "gridconv+"]),                      # a set spanning three chunks
+    (2, 333, 72, [0, 20, 0, 3], ["gridconv", "gridconv+", "gridconv", "mask"]),  # empty sets, C not a multiple of 64
+    (5, 200, 128, [1] * 40, ["mask"] * 40),                                      # many tiny sets
+    (40, 1369, 256, [100, 7], ["gridconv", "gridconv+"]),                        # more tiles than SMs
+])
+def test_match_tensor_core_vs_cuda_core(Q, HW, C, counts, modes):
+    """the tcgen05 split-bf16 kernel agrees with the exact-fp32 kernel far inside the 1e-3 budget"""
+    rng = np.random.default_rng(Q * 1000 + HW + C)
+    cap = max(max(counts), 1) + 3
+    pr = _fake_protos(rng, counts, modes, cap, C)
+    qry = _t((rng.standard_normal((Q, HW, C)) * rng.uniform(0.1, 5.0, (Q, HW, 1))).astype(np.float32))
+    # make some queries close to a prototype so that the softmax is peaked, and one all-zero row
+    qry[0, : min(HW, 50)] += 4.0 * pr["protos"][-1, 0]
+    qry[-1, HW - 1] = 0.0
+    s1, a1, _ = ops.alp_match(qry, pr, want_assign=True, algo=1)
+    st1 = pr["status"].clone()
+    pr["status"].zero_()
+    s2, a2, _ = ops.alp_match(qry, pr, want_assign=True, algo=2)
+    torch.cuda.synchronize()
+    assert torch.equal(st1, pr["status"])
+    s1, s2, a1, a2 = s1.cpu().numpy(), s2.cpu().numpy(), a1.cpu().numpy(), a2.cpu().numpy()
+    for i, (c, m) in enumerate(zip(counts, modes)):
+        if c == 0:
+            assert np.isnan(s2[:, i]).all() and np.isnan(a2[:, i]).all()
+            continue
+        np.testing.assert_allclose(s2[:, i], s1[:, i], atol=1e-4, rtol=0)
+        if m == "mask":
+            np.testing.assert_allclose(a2[:, i], a1[:, i], atol=1e-4, rtol=0)
+        else:
+            # argmax may differ only between near-tied prototypes
+            bad = np.argwhere(a1[:, i] != a2[:, i])
+            assert len(bad) <= 0.001 * a1[:, i].size + 2
+    # auto (algo 0) takes the tensor-core path for these shapes: identical bits to algo 2
+    s0, _, _ = ops.alp_match(qry, pr, want_assign=False, algo=0)
+    assert np.array_equal(s0.cpu().numpy(), s2, equal_nan=True)
+
+
+def test_match_auto_falls_back_to_cuda_cores_for_sims_and_odd_channels():
+    rng = np.random.default_rng(5)
+    pr = _fake_protos(rng, [10, 3], ["gridconv", "gridconv+"], 12, 20)      # C = 20: not a multiple of 8
+    qry = _t(rng.standard_normal((1, 50, 20)).astype(np.float32))
+    s0, _, _ = ops.alp_match(qry, pr, algo=0)
+    s1, _, _ = ops.alp_match(qry, pr, algo=1)
+    assert torch.equal(s0, s1)
+    with pytest.raises(RuntimeError):
+        ops.alp_match(qry, pr, algo=2)
+    pr = _fake_protos(rng, [10, 3], ["gridconv", "gridconv+"], 12, 64)
+    qry = _t(rng.standard_normal((1, 50, 64)).astype(np.float32))
+    s0, _, sims0 = ops.alp_match(qry, pr, want_sims=True, algo=0)
+    s1, _, sims1 = ops.alp_match(qry, pr, want_sims=True, algo=1)
+    assert torch.equal(s0, s1) and torch.equal(sims0[:, 0, :10], sims1[:, 0, :10])
