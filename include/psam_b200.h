@@ -58,6 +58,12 @@ const char* psam_last_error(void);
 /* Number of kernels this library has launched on the calling process so far (bench.py's
  * gpu_launches claim is read from here). */
 uint64_t psam_launch_count(void);
+/* Optional per-kernel device timing for bench.py's roofline: while enabled, every kernel launch of the
+ * library is bracketed by a CUDA event pair on its stream.  psam_profile_collect synchronises on those
+ * events, returns the number of distinct kernels seen since the last collect and fills, in first-launch
+ * order, their newline-separated names, accumulated milliseconds and launch counts. */
+void psam_profile_enable(int on);
+int psam_profile_collect(char* names, size_t names_bytes, float* total_ms, int32_t* launches, int max_kernels);
 
 /* --------------------------------------------------------------------------------------
  * Kernel 1 -- prototypes.  Replaces MultiProtoAsConv.get_prototypes + safe_norm

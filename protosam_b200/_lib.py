@@ -32,6 +32,8 @@ SIGNATURES = {
     "psam_abi_version": (c_i, []),
     "psam_last_error": (ctypes.c_char_p, []),
     "psam_launch_count": (ctypes.c_uint64, []),
+    "psam_profile_enable": (None, [c_i]),
+    "psam_profile_collect": (c_i, [c_p, c_sz, c_p, c_p, c_i]),
     "psam_alp_prototypes_workspace": (c_sz, [c_i] * 7),
     "psam_alp_prototypes": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
@@ -78,3 +80,17 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().psam_launch_count())
+
+
+def profile_enable(on: bool):
+    load().psam_profile_enable(1 if on else 0)
+
+
+def profile_collect(max_kernels: int = 64) -> dict:
+    """-> {kernel name: (total ms, launches)} since the last collect (synchronises on the recorded events)."""
+    names = ctypes.create_string_buffer(64 * max_kernels)
+    ms = (ctypes.c_float * max_kernels)()
+    cnt = (ctypes.c_int32 * max_kernels)()
+    n = load().psam_profile_collect(names, len(names), ms, cnt, max_kernels)
+    keys = names.value.decode().split("\n")[:n]
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(keys)}

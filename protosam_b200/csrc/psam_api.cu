@@ -2,6 +2,11 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "psam_common.cuh"
 
@@ -20,6 +25,35 @@ void set_error(const char* fmt, ...)
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+// ---- optional per-kernel timing: one CUDA event pair around every launch of this library ----
+bool g_profiling = false;
+struct ProfSpan {
+    const char* what;
+    cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfSpan> g_spans;
+static thread_local cudaEvent_t t_pending = nullptr;
+
+void prof_begin(cudaStream_t stream)
+{
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, stream);
+    t_pending = e;
+}
+
+void prof_end(const char* what, cudaStream_t stream)
+{
+    if (!t_pending) return;
+    cudaEvent_t e1;
+    if (cudaEventCreate(&e1) != cudaSuccess) return;
+    cudaEventRecord(e1, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_spans.push_back({what, t_pending, e1});
+    t_pending = nullptr;
+}
+
 }  // namespace psam
 
 static_assert(sizeof(psam_prompt_rec) == 96, "psam_prompt_rec layout is part of the ABI");
@@ -28,3 +62,44 @@ static_assert(sizeof(psam_image_hdr) == 64, "psam_image_hdr layout is part of th
 extern "C" int psam_abi_version(void) { return PSAM_ABI_VERSION; }
 extern "C" const char* psam_last_error(void) { return psam::g_err; }
 extern "C" uint64_t psam_launch_count(void) { return psam::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" void psam_profile_enable(int on)
+{
+    psam::g_profiling = on != 0;
+}
+
+extern "C" int psam_profile_collect(char* names, size_t names_bytes, float* total_ms, int32_t* launches, int max_kernels)
+{
+    using namespace psam;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::vector<std::string> order;
+    std::map<std::string, std::pair<double, int>> agg;
+    for (ProfSpan& s : g_spans) {
+        float ms = 0.f;
+        cudaEventSynchronize(s.e1);
+        if (cudaEventElapsedTime(&ms, s.e0, s.e1) == cudaSuccess) {
+            auto it = agg.find(s.what);
+            if (it == agg.end()) { order.push_back(s.what); agg[s.what] = {ms, 1}; }
+            else { it->second.first += ms; it->second.second += 1; }
+        }
+        cudaEventDestroy(s.e0);
+        cudaEventDestroy(s.e1);
+    }
+    g_spans.clear();
+    int n = 0;
+    size_t off = 0;
+    if (names && names_bytes) names[0] = 0;
+    for (const std::string& k : order) {
+        if (n >= max_kernels) break;
+        if (names && off + k.size() + 2 < names_bytes) {
+            memcpy(names + off, k.c_str(), k.size());
+            off += k.size();
+            names[off++] = '\n';
+            names[off] = 0;
+        }
+        if (total_ms) total_ms[n] = (float)agg[k].first;
+        if (launches) launches[n] = agg[k].second;
+        ++n;
+    }
+    return n;
+}

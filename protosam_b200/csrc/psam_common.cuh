@@ -12,6 +12,14 @@ namespace psam {
 // ---- host-side error plumbing (thread-local message, see psam_last_error) ----
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// per-kernel device timing (psam_profile_enable / psam_profile_collect): events around every launch
+extern bool g_profiling;
+void prof_begin(cudaStream_t stream);
+void prof_end(const char* what, cudaStream_t stream);
+#define PSAM_PROF_BEGIN(stream)                      \
+    do {                                             \
+        if (psam::g_profiling) psam::prof_begin(stream); \
+    } while (0)
 
 #define PSAM_CHECK_ARG(cond, ...)                     \
     do {                                              \
@@ -29,6 +37,7 @@ void count_launch(int n = 1);
             return PSAM_ERR_LAUNCH;                                                    \
         }                                                                              \
         psam::count_launch();                                                          \
+        if (psam::g_profiling) psam::prof_end(what, stream);                           \
     } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -625,6 +625,7 @@ extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, cons
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PSAM_ERR_LAUNCH; }
         attr_done = true;
     }
+    PSAM_PROF_BEGIN(stream);
     k_components<<<ctas, CT, dyn, stream>>>(P);
     PSAM_CHECK_LAUNCH("k_components");
     return PSAM_OK;

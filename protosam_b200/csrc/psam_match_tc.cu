@@ -522,9 +522,12 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     uint8_t* b_img = a_img + align_up(L.a_bytes, 1024);
     float* scale = reinterpret_cast<float*>(b_img + align_up(L.b_bytes, 1024));
 
+    PSAM_PROF_BEGIN(stream);
+
     k_pack_protos<<<dim3(pad16(p.cap_rows) / 8, p.nsets), 256, 0, stream>>>(p.protos, p.cap_rows, p.counts, p.C, L.KB, L.G,
                                                                            b_img);
     PSAM_CHECK_LAUNCH("k_pack_protos");
+    PSAM_PROF_BEGIN(stream);
     k_pack_query<<<L.ntiles * BM / 8, 256, 0, stream>>>(p.qry, p.slice_stride, p.row_stride, p.HW, L.R, p.C, L.KB, a_img,
                                                        scale);
     PSAM_CHECK_LAUNCH("k_pack_query");
@@ -544,6 +547,7 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     TcParams t{a_img, b_img, scale, p.counts, p.eff_modes, p.scores, p.assign, p.status,
                p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit};
     const int grid = min(sms, L.ntiles * nsplit);
+    PSAM_PROF_BEGIN(stream);
     k_match_tc<<<grid, THREADS, SMEM_BYTES, stream>>>(t);
     PSAM_CHECK_LAUNCH("k_match_tc");
     return PSAM_OK;

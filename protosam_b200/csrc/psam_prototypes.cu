@@ -353,17 +353,22 @@ extern "C" int psam_alp_prototypes(const float* sup_x, const int64_t* xs, const 
     int32_t* plocal = cv.take<int32_t>(nsets);
     float* partial = cv.take<float>((size_t)nsets * S * h * C);
 
+    PSAM_PROF_BEGIN(stream);
+
     k_pool_mask<<<nsets, 256, 0, stream>>>(sup_y, modes, S, h, w, kh, kw, auto_kh, auto_kw, thresh, pooled, survive,
                                            rowidx, ysum, counts, eff_modes, status, plocal);
     PSAM_CHECK_LAUNCH("k_pool_mask");
     if (N > 0) {
+        PSAM_PROF_BEGIN(stream);
         k_pool_feat<<<dim3(N, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], rowidx, S, C, h, w, kh, kw,
                                                         cap_rows, protos);
         PSAM_CHECK_LAUNCH("k_pool_feat");
     }
+    PSAM_PROF_BEGIN(stream);
     k_global_partial<<<dim3(h, S, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], sup_y, eff_modes, S, C,
                                                             h, w, partial);
     PSAM_CHECK_LAUNCH("k_global_partial");
+    PSAM_PROF_BEGIN(stream);
     k_global_final<<<dim3(S, nsets), 256, 0, stream>>>(partial, ysum, eff_modes, plocal, S, C, h, cap_rows, protos);
     PSAM_CHECK_LAUNCH("k_global_final");
     return PSAM_OK;
@@ -382,6 +387,7 @@ extern "C" int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, i
     size_t smem = N * sizeof(int32_t);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_proto_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PSAM_PROF_BEGIN(stream);
     k_proto_grid<<<1, 256, smem, stream>>>(pooled, S, gh, gw, vw, thresh, mode, out, nullptr);
     PSAM_CHECK_LAUNCH("k_proto_grid");
     return PSAM_OK;

@@ -150,9 +150,6 @@ class CoarseVolumeEngine:
         """-> (hdr, recs) on the device; image index = q*L + l."""
         return self.prompts_from_logits(self.match(qry_feats))
 
-    def match_kernel_name(self) -> str:
-        return {0: "k_match_simt (auto)", 1: "k_match_simt", 2: "k_match_tc"}.get(self.match_algo, "?")
-
     def run_sharded(self, qry_local: torch.Tensor, q_total: int, dst: int = 0):
         """This rank's block of a Q-slice volume (see shard_range) -> gathered records on `dst`."""
         world, _ = self._world()
