@@ -411,3 +411,62 @@ def test_match_auto_falls_back_to_cuda_cores_for_sims_and_odd_channels():
     s0, _, sims0 = ops.alp_match(qry, pr, want_sims=True, algo=0)
     s1, _, sims1 = ops.alp_match(qry, pr, want_sims=True, algo=1)
     assert torch.equal(s0, s1) and torch.equal(sims0[:, 0, :10], sims1[:, 0, :10])
+
+
+# ------------------------------------------------------------------------------ remaining BASELINE configs
+
+def _oracle_logits(vol, cfg, ws, q, l, fg_mode, ks):
+    sup_x = np.transpose(vol.sup, (0, 3, 1, 2))[None, :, None]
+    qry = np.transpose(vol.qry[q], (2, 0, 1))[None]
+    bg, _, _, _ = O.alp_forward(qry, sup_x, vol.bg[l][None, :, None], "gridconv", 0.95, ks, isval=True, val_wsize=ws)
+    fg, _, _, _ = O.alp_forward(qry, sup_x, vol.fg[l][None, :, None], fg_mode, 0.95, ks, isval=True, val_wsize=ws)
+    return np.concatenate([bg, fg], 1)[0]
+
+
+@pytest.mark.parametrize("ws", [2, 3, 4, 5, 6, 7, 8])
+def test_cfg5_window_sweep_vs_oracle(ws):
+    """BASELINE config 5 (ViT-L/14 1024-d, 48x48, grid window 2..8, 'gridconv+') at 2 slices: maps within 1e-3 of the
+    oracle, prompts bit-exact on the GPU's own maps."""
+    cfg = synth.CONFIGS["cfg5_stress_vitl"]
+    vol = synth.make_volume(50 + ws, Q=2, L=1, C=cfg["C"], h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=ws, fg_mode="gridconv+")
+    pr = eng.set_support(_t(vol.sup), _t(vol.fg))
+    q = _t(vol.qry)
+    logits = eng.match(q).cpu().numpy()
+    ks = [cfg["h"] // 8, cfg["w"] // 8]
+    sup_x = np.transpose(vol.sup, (0, 3, 1, 2))
+    for name, mask, mode, si in (("bg", vol.bg[0], "gridconv", 0), ("fg", vol.fg[0], "gridconv+", 1)):
+        ref = O.get_prototypes(sup_x, mask[:, None], mode, (ws, ws), 0.95)
+        assert np.array_equal(ref["survive"], pr["survive"][si, : pr["N"]].cpu().numpy().astype(bool)), name
+    got = eng.decode(*eng.run(q))
+    for qi in range(2):
+        ref = _oracle_logits(vol, cfg, ws, qi, 0, "gridconv+", ks)
+        np.testing.assert_allclose(logits[qi], ref, atol=MAP_TOL, rtol=0)
+        rp = O.coarse_to_prompts(logits[qi][None], cfg["img_size"], 1024, use_cca=False, point_mode="both")
+        s = got[qi][0]
+        assert s.empty == rp["empty"]
+        if not s.empty:
+            assert np.array_equal(s.boxes, rp["bboxes"]) and np.array_equal(s.points, rp["points"])
+
+
+@pytest.mark.parametrize("hw", [48, 73])
+@pytest.mark.parametrize("point_mode", ["conf", "both"])
+def test_cfg4_polyp_mask_and_gridconv_single_stage(hw, point_mode):
+    """BASELINE config 4: fg forced to 'mask' (small lesion), bg 'gridconv', logits upsampled straight to 1024."""
+    cfg = synth.CONFIGS["cfg4_polyp_1024"]
+    vol = synth.make_volume(404 + hw, Q=2, L=1, C=cfg["C"], h=hw, w=hw, img_size=1024)
+    eng = CoarseVolumeEngine((hw, hw), 1024, out_size=1024, val_wsize=2, fg_mode="mask", point_mode=point_mode)
+    eng.set_support(_t(vol.sup), _t(vol.fg))
+    q = _t(vol.qry)
+    logits = eng.match(q).cpu().numpy()
+    got = eng.decode(*eng.run(q))
+    cfg2 = dict(cfg, h=hw, w=hw)
+    for qi in range(2):
+        ref = _oracle_logits(vol, cfg2, 2, qi, 0, "mask", [hw // 8, hw // 8])
+        np.testing.assert_allclose(logits[qi], ref, atol=MAP_TOL, rtol=0)
+        rp = O.coarse_to_prompts(logits[qi][None], 1024, 1024, use_cca=False, point_mode=point_mode)
+        s = got[qi][0]
+        assert s.empty == rp["empty"]
+        if not s.empty:
+            assert np.array_equal(s.boxes, rp["bboxes"])
+            assert np.array_equal(s.points, rp["points"]) and s.points.dtype == rp["points"].dtype
