@@ -70,7 +70,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=self.fh,
+                                          "-i", str(self.gpu_index), "-lms", "50"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -264,12 +264,15 @@ def gpu_arm(args, cfg):
     ms_step = float(t.item()) / K
     ms_match = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     ms_prompt = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    # keep the same load running briefly if the timed region was too short for clock samples
+    # keep the same kernels running briefly if the timed region was too short for clock samples (rank-local work
+    # only: no collective may be entered by a subset of the ranks)
     if rank == 0 and sampler.mark() - line0 < 3:
         t_end_probe = time.time() + 1.0
         i = 0
         while time.time() < t_end_probe:
-            step(i); i += 1
+            eng.run(qvols[i % N_ROTATE]); i += 1
+            if i % 20 == 0:
+                torch.cuda.synchronize()
         torch.cuda.synchronize()
     clocks = sampler.stop(line0) if rank == 0 else None
 
@@ -405,7 +408,7 @@ def gpu_arm(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", type=int, default=0, help="match kernel: 0 auto, 1 fp32 CUDA cores, 2 tcgen05")
