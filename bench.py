@@ -216,7 +216,11 @@ def gpu_arm(args, cfg):
                              point_mode="both", match_algo=args.algo)
     q_total = Q * world
 
+    pending = [None]
+
     def step(i, ev=None):
+        """One volume: prototypes (+ broadcast), match, prompts, record gather.  The gather of step i is
+        asynchronous (NCCL's stream) and is waited for at the start of step i+1 / at the end of the region."""
         eng.set_support(sup, fg)
         qv = qvols[i % N_ROTATE]
         if ev is not None:
@@ -224,16 +228,31 @@ def gpu_arm(args, cfg):
         logits = eng.match(qv)
         if ev is not None:
             ev[1].record()
-        hdr, recs = eng.prompts_from_logits(logits)
+        if world == 1:
+            out = eng.prompts_from_logits(logits)
+            if ev is not None:
+                ev[2].record()
+            return out
+        counts = [(b - a) * L for a, b in (shard_range(q_total, world, r) for r in range(world))]
+        _, _, buf = eng.prompts_from_logits(logits, n_alloc=max(counts), return_packed=True)
         if ev is not None:
             ev[2].record()
-        if world > 1:
-            counts = [(b - a) * L for a, b in (shard_range(q_total, world, r) for r in range(world))]
-            from protosam_b200.engine import gather_records
-            hdr, recs = gather_records(hdr, recs, counts, dst=0)
-        return hdr, recs
+        if pending[0] is not None:
+            pending[0].result()
+        from protosam_b200.engine import gather_packed
+        pending[0] = gather_packed(buf, counts, eng.max_cc, dst=0, async_op=True)
+        return pending[0]
+
+    def finish(out):
+        """(hdr, recs) of a step's return value (waits for its gather)"""
+        if world == 1:
+            return out
+        return out.result()
 
     def sync_all():
+        if pending[0] is not None:
+            pending[0].result()
+            pending[0] = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -254,6 +273,9 @@ def gpu_arm(args, cfg):
     t_start.record()
     for i in range(K):
         step(i, evs[i])
+    if pending[0] is not None:          # the last gather is part of the timed region
+        pending[0].result()
+        pending[0] = None
     t_end.record()
     sync_all()
     launches = _lib.launch_count() - n0
@@ -281,7 +303,9 @@ def gpu_arm(args, cfg):
     _lib.profile_collect()
     _lib.profile_enable(True)
     for i in range(Kp):
-        hdr_p, recs_p = step(i)
+        out_p = step(i)
+    hdr_p, recs_p = finish(out_p)
+    pending[0] = None
     torch.cuda.synchronize()
     _lib.profile_enable(False)
     prof = {k: (ms / Kp, n // Kp) for k, (ms, n) in _lib.profile_collect().items()}   # ms per step, launches per step
@@ -293,7 +317,8 @@ def gpu_arm(args, cfg):
     h_fg = torch.from_numpy(vol.fg).pin_memory()
     h_q = [q.cpu().pin_memory() for q in qvols]
     d_sup, d_fg, d_q = torch.empty_like(sup), torch.empty_like(fg), torch.empty_like(base)
-    hdr, recs = step(0)
+    hdr, recs = finish(step(0))
+    pending[0] = None
     n_img = Q * L
     h_hdr = torch.empty((n_img, 64), dtype=torch.uint8).pin_memory()
     h_rec = torch.empty((n_img, eng.max_cc, 96), dtype=torch.uint8).pin_memory()

@@ -38,13 +38,54 @@ _PROTO_KEYS = ("protos", "counts", "eff_modes", "status")
 
 
 def broadcast_prototypes(protos: dict, src: int = 0, group=None) -> dict:
-    """Broadcast the packed prototype tables from `src` (NCCL over NVLink on the GPU box; the same
-    code runs over gloo in the CPU tests).  Shapes are rank-independent, so receivers pre-allocate."""
+    """Broadcast the prototype table from `src` (NCCL over NVLink on the GPU box; the same code runs over
+    gloo in the CPU tests).  Shapes are rank-independent, so receivers pre-allocate; tables built by
+    ops.proto_table_alloc live in one buffer and move with ONE collective."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return protos
+    if protos.get("packed") is not None:
+        dist.broadcast(protos["packed"], src=src, group=group)
         return protos
     for k in _PROTO_KEYS:
         dist.broadcast(protos[k], src=src, group=group)
     return protos
+
+
+class PendingGather:
+    """Handle of an in-flight record gather (NCCL runs it on its own stream, so the next volume's kernels
+    overlap it).  result() waits and returns (hdr_all, recs_all) on dst, (None, None) elsewhere."""
+
+    def __init__(self, work, bucket, counts, max_cc, keep):
+        self.work, self.bucket, self.counts, self.max_cc, self.keep = work, bucket, counts, max_cc, keep
+        self._ready = None
+
+    @classmethod
+    def done(cls, pair):
+        p = cls(None, None, [], 0, None)
+        p._ready = pair
+        return p
+
+    def result(self):
+        if self._ready is not None:
+            return self._ready
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        if self.bucket is None:
+            return None, None
+        parts = [ops.split_records(b, self.max_cc) for b in self.bucket]
+        return (torch.cat([h[:c] for (h, _), c in zip(parts, self.counts)], 0),
+                torch.cat([r[:c] for (_, r), c in zip(parts, self.counts)], 0))
+
+
+def gather_packed(buf: torch.Tensor, counts: Sequence[int], max_cc: int, dst: int = 0, group=None,
+                  async_op: bool = False):
+    """ONE gather of the per-rank packed (headers | records) buffers, all sized for max(counts) images."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bucket = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    work = dist.gather(buf, bucket, dst=dst, group=group, async_op=async_op)
+    pend = PendingGather(work if async_op else None, bucket, list(counts), max_cc, buf)
+    return pend if async_op else pend.result()
 
 
 def gather_records(hdr: torch.Tensor, recs: torch.Tensor, counts: Sequence[int], dst: int = 0, group=None):
@@ -53,23 +94,11 @@ def gather_records(hdr: torch.Tensor, recs: torch.Tensor, counts: Sequence[int],
     (None, None) elsewhere."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return hdr, recs
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    nmax = max(counts)
-
-    def pad(t):
-        if t.shape[0] == nmax:
-            return t.contiguous()
-        out = t.new_zeros((nmax,) + tuple(t.shape[1:]))
-        out[: t.shape[0]] = t
-        return out
-
-    outs = []
-    for t in (hdr, recs):
-        tp = pad(t)
-        bucket = [torch.empty_like(tp) for _ in range(world)] if rank == dst else None
-        dist.gather(tp, bucket, dst=dst, group=group)
-        outs.append(torch.cat([b[:c] for b, c in zip(bucket, counts)], 0) if rank == dst else None)
-    return outs[0], outs[1]
+    nmax, max_cc = max(counts), recs.shape[1]
+    buf, h, r = ops.records_alloc(nmax, max_cc, hdr.device)
+    h[: hdr.shape[0]] = hdr
+    r[: recs.shape[0]] = recs
+    return gather_packed(buf, counts, max_cc, dst=dst, group=group)
 
 
 class CoarseVolumeEngine:
@@ -120,12 +149,8 @@ class CoarseVolumeEngine:
         else:
             gh, gw = h // self.val_wsize, w // self.val_wsize
             N = S * gh * gw
-            dev = sup_feats.device
-            protos = dict(protos=torch.empty((2 * L, N + S, C), dtype=torch.float32, device=dev),
-                          counts=torch.empty(2 * L, dtype=torch.int32, device=dev),
-                          eff_modes=torch.empty(2 * L, dtype=torch.int32, device=dev),
-                          status=torch.empty(2 * L, dtype=torch.int32, device=dev),
-                          cap_rows=N + S, N=N, gh=gh, gw=gw, S=S, C=C)
+            protos = ops.proto_table_alloc(2 * L, N + S, C, sup_feats.device)
+            protos.update(N=N, gh=gh, gw=gw, S=S, C=C)
         self.protos = broadcast_prototypes(protos, src=src, group=self.group)
         return self.protos
 
@@ -137,25 +162,29 @@ class CoarseVolumeEngine:
                                      algo=self.match_algo)
         return scores.view(Q * self.n_labels, 2, h, w)
 
-    def prompts_from_logits(self, logits: torch.Tensor):
+    def prompts_from_logits(self, logits: torch.Tensor, n_alloc=None, return_packed=False):
         """coarse logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on the device."""
         n = logits.shape[0]
         need = ops._lib.load().psam_coarse_to_prompts_workspace(n, self.out_size, self.max_runs, self.max_cc)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=logits.device)
         return ops.coarse_to_prompts(logits, self.img_size, self.out_size, self.use_cca, self.max_cc,
-                                     self.max_runs, workspace=self._ws)
+                                     self.max_runs, workspace=self._ws, n_alloc=n_alloc, return_packed=return_packed)
 
     def run(self, qry_feats: torch.Tensor):
         """-> (hdr, recs) on the device; image index = q*L + l."""
         return self.prompts_from_logits(self.match(qry_feats))
 
-    def run_sharded(self, qry_local: torch.Tensor, q_total: int, dst: int = 0):
-        """This rank's block of a Q-slice volume (see shard_range) -> gathered records on `dst`."""
+    def run_sharded(self, qry_local: torch.Tensor, q_total: int, dst: int = 0, async_op: bool = False):
+        """This rank's block of a Q-slice volume (see shard_range) -> gathered records on `dst`: (hdr, recs), or a
+        PendingGather when async_op (its result() gives the same pair)."""
         world, _ = self._world()
-        hdr, recs = self.run(qry_local)
         counts = [(hi - lo) * self.n_labels for lo, hi in (shard_range(q_total, world, r) for r in range(world))]
-        return gather_records(hdr, recs, counts, dst=dst, group=self.group)
+        if world == 1:
+            out = self.run(qry_local)
+            return PendingGather.done(out) if async_op else out
+        _, _, buf = self.prompts_from_logits(self.match(qry_local), n_alloc=max(counts), return_packed=True)
+        return gather_packed(buf, counts, self.max_cc, dst=dst, group=self.group, async_op=async_op)
 
     def decode(self, hdr: torch.Tensor, recs: torch.Tensor) -> List[List[P.SlicePrompts]]:
         """Device records -> per slice, per label prompt objects (one D2H copy)."""

@@ -51,6 +51,20 @@ def _ws(nbytes, device):
 
 # ------------------------------------------------------------------ kernel 1
 
+def proto_table_alloc(nsets, cap_rows, C, device):
+    """The prototype table of psam_alp_prototypes as views of ONE byte buffer (`packed`), so that the multi-GPU
+    path moves it with a single broadcast: protos [nsets,cap,C] f32 | counts | eff_modes | status [nsets] i32."""
+    def up(x):
+        return (x + 255) // 256 * 256
+    nb_p, nb_i = up(nsets * cap_rows * C * 4), up(nsets * 4)
+    packed = torch.empty(nb_p + 3 * nb_i, dtype=torch.uint8, device=device)
+
+    def ints(k):
+        return packed[nb_p + k * nb_i: nb_p + k * nb_i + nsets * 4].view(torch.int32)
+    return dict(packed=packed, protos=packed[: nsets * cap_rows * C * 4].view(torch.float32).view(nsets, cap_rows, C),
+                counts=ints(0), eff_modes=ints(1), status=ints(2), cap_rows=cap_rows)
+
+
 def alp_prototypes(sup_x, sup_y, modes, ksize, thresh, auto_ksize=None):
     """sup_x [S,C,h,w] (any strides; channels-last is the fast case), sup_y [nsets,S,h,w],
     modes: list of 'mask' | 'gridconv' | 'gridconv+' | 'auto_fg'.  Returns a dict of device
@@ -67,14 +81,11 @@ def alp_prototypes(sup_x, sup_y, modes, ksize, thresh, auto_ksize=None):
     N = S * gh * gw
     cap = N + S
     dev = sup_x.device
-    out = dict(
-        protos=torch.empty((nsets, cap, C), dtype=torch.float32, device=dev),
-        counts=torch.empty(nsets, dtype=torch.int32, device=dev),
-        eff_modes=torch.empty(nsets, dtype=torch.int32, device=dev),
-        status=torch.empty(nsets, dtype=torch.int32, device=dev),
+    out = proto_table_alloc(nsets, cap, C, dev)
+    out.update(
         survive=torch.empty((nsets, max(N, 1)), dtype=torch.uint8, device=dev),
         pooled=torch.empty((nsets, max(N, 1)), dtype=torch.float32, device=dev),
-        cap_rows=cap, N=N, gh=gh, gw=gw, S=S, C=C,
+        N=N, gh=gh, gw=gw, S=S, C=C,
     )
     ws = _ws(L.psam_alp_prototypes_workspace(nsets, S, C, h, w, kh, kw), dev)
     strides = (ctypes.c_int64 * 4)(*sup_x.stride())
@@ -164,23 +175,40 @@ def components(maskbits, p_fg, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DE
     return hdr, recs, labels
 
 
+def records_alloc(n_alloc, max_cc, device):
+    """Headers [n,64] and records [n,max_cc,96] as views of ONE zeroed byte buffer (one gather moves both)."""
+    buf = torch.zeros(n_alloc * (HDR_DTYPE.itemsize + max_cc * REC_DTYPE.itemsize), dtype=torch.uint8, device=device)
+    hdr = buf[: n_alloc * HDR_DTYPE.itemsize].view(n_alloc, HDR_DTYPE.itemsize)
+    recs = buf[n_alloc * HDR_DTYPE.itemsize:].view(n_alloc, max_cc, REC_DTYPE.itemsize)
+    return buf, hdr, recs
+
+
+def split_records(buf, max_cc):
+    """inverse of records_alloc's layout for a received buffer"""
+    n_alloc = buf.numel() // (HDR_DTYPE.itemsize + max_cc * REC_DTYPE.itemsize)
+    return (buf[: n_alloc * HDR_DTYPE.itemsize].view(n_alloc, HDR_DTYPE.itemsize),
+            buf[n_alloc * HDR_DTYPE.itemsize:].view(n_alloc, max_cc, REC_DTYPE.itemsize))
+
+
 def coarse_to_prompts(logits, mid, out=1024, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DEFAULT_MAX_RUNS,
-                      workspace=None):
-    """logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on device, one call."""
+                      workspace=None, n_alloc=None, return_packed=False):
+    """logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on device, one call.  n_alloc >= n sizes
+    the (zero-padded) output buffer, e.g. to the largest shard of a multi-GPU run."""
     L = _lib.load()
     _need_cuda(logits)
     logits = logits.contiguous()
     n, two, h, w = logits.shape
     assert two == 2
     dev = logits.device
-    hdr = torch.zeros((n, HDR_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    recs = torch.zeros((n, max_cc, REC_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    buf, hdr, recs = records_alloc(max(n_alloc or n, n), max_cc, dev)
     need = L.psam_coarse_to_prompts_workspace(n, out, max_runs, max_cc)
     ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
     rc = L.psam_coarse_to_prompts(_ptr(logits), n, h, w, int(mid), int(out), int(bool(use_cca)), max_cc, max_runs,
                                   _ptr(hdr), _ptr(recs), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "psam_coarse_to_prompts")
-    return hdr, recs
+    if return_packed:
+        return hdr[:n], recs[:n], buf
+    return hdr[:n], recs[:n]
 
 
 def decode_headers(hdr_u8) -> np.ndarray:

@@ -49,6 +49,24 @@ def _worker(rank, world, port, q_total, L, out_q):
         tr = torch.from_numpy(recs.view(np.uint8).reshape(n_local, max_cc, 96).copy())
         counts = [(b - a) * L for a, b in (engine.shard_range(q_total, world, r) for r in range(world))]
         H, R = engine.gather_records(th, tr, counts, dst=0)
+        # 3) the engine's own layout: ONE packed table broadcast, ONE packed asynchronous gather
+        tab = ops.proto_table_alloc(nsets, cap, C, "cpu")
+        if rank == 0:
+            for k in ("protos", "counts", "eff_modes", "status"):
+                tab[k].copy_(truth[k])
+        else:
+            tab["packed"].zero_()
+        engine.broadcast_prototypes(tab, src=0)
+        ok_bcast &= all(torch.equal(tab[k], truth[k]) for k in truth)
+        buf, bh, br = ops.records_alloc(max(counts), max_cc, "cpu")
+        bh[:n_local] = th
+        br[:n_local] = tr
+        pend = engine.gather_packed(buf, counts, max_cc, dst=0, async_op=True)
+        H2, R2 = pend.result()
+        if rank == 0:
+            ok_bcast &= torch.equal(H2, H) and torch.equal(R2, R)
+        else:
+            ok_bcast &= H2 is None and R2 is None
         if rank == 0:
             Hn, Rn = ops.decode_headers(H), ops.decode_records(R)
             ok = len(Hn) == q_total * L
