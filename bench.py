@@ -50,6 +50,7 @@ def workload_desc(cfg, n_gpus):
                      f"({N_ROTATE * cfg['Q'] * cfg['h'] * cfg['w'] * cfg['C'] * 4 / 1e6:.0f} MB of inputs + "
                      f"{cfg['Q'] * cfg['L'] * 4.2:.0f} MB of per-step intermediates > 126 MB L2)",
         "parallelism": f"slices sharded over {n_gpus} GPU(s); prototype broadcast + record gather",
+        "lanes": f"{cfg.get('lanes', 1)} volume(s) in flight per GPU on separate CUDA streams",
     }
 
 
@@ -191,7 +192,7 @@ def gpu_arm(args, cfg):
     import torch.distributed as dist
 
     from protosam_b200 import _lib, ops, synth
-    from protosam_b200.engine import CoarseVolumeEngine, shard_range
+    from protosam_b200.engine import CoarseVolumeEngine, gather_packed, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,6 +201,8 @@ def gpu_arm(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -212,47 +215,61 @@ def gpu_arm(args, cfg):
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     qvols = [base] + [(base.roll(k + 1, 0) + 0.05 * torch.randn(base.shape, generator=g, device=dev)).contiguous()
                       for k in range(N_ROTATE - 1)]
-    eng = CoarseVolumeEngine((h, w), cfg["img_size"], out_size=1024, val_wsize=cfg["ws"], use_cca=False,
-                             point_mode="both", match_algo=args.algo)
+    NL = max(1, args.lanes)
+    engs = [CoarseVolumeEngine((h, w), cfg["img_size"], out_size=1024, val_wsize=cfg["ws"], use_cca=False,
+                               point_mode="both", match_algo=args.algo) for _ in range(NL)]
+    eng = engs[0]
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]
     q_total = Q * world
+    counts_all = [(b - a) * L for a, b in (shard_range(q_total, world, r) for r in range(world))]
+    pending = [None] * NL
 
-    pending = [None]
-
-    def step(i, ev=None):
-        """One volume: prototypes (+ broadcast), match, prompts, record gather.  The gather of step i is
-        asynchronous (NCCL's stream) and is waited for at the start of step i+1 / at the end of the region."""
-        eng.set_support(sup, fg)
-        qv = qvols[i % N_ROTATE]
-        if ev is not None:
-            ev[0].record()
-        logits = eng.match(qv)
-        if ev is not None:
-            ev[1].record()
-        if world == 1:
-            out = eng.prompts_from_logits(logits)
+    def step(i, ev=None, lane=None):
+        """One volume: prototypes (+ broadcast), match, prompts, record gather, all on the stream of lane
+        i % NL: consecutive volumes are in flight on different streams, so the small launches, the collectives
+        and the tail of one volume overlap the big kernels of the next.  The gather of a volume is asynchronous
+        (NCCL's stream) and is waited for when its lane is used again / at the end of the region."""
+        ln = i % NL if lane is None else lane
+        e = engs[ln]
+        with torch.cuda.stream(lanes[ln]):
+            e.set_support(sup, fg)
+            qv = qvols[i % N_ROTATE]
+            if ev is not None:
+                ev[0].record()
+            logits = e.match(qv)
+            if ev is not None:
+                ev[1].record()
+            if world == 1:
+                out = e.prompts_from_logits(logits)
+                if ev is not None:
+                    ev[2].record()
+                return out
+            _, _, buf = e.prompts_from_logits(logits, n_alloc=max(counts_all), return_packed=True)
             if ev is not None:
                 ev[2].record()
-            return out
-        counts = [(b - a) * L for a, b in (shard_range(q_total, world, r) for r in range(world))]
-        _, _, buf = eng.prompts_from_logits(logits, n_alloc=max(counts), return_packed=True)
-        if ev is not None:
-            ev[2].record()
-        if pending[0] is not None:
-            pending[0].result()
-        from protosam_b200.engine import gather_packed
-        pending[0] = gather_packed(buf, counts, eng.max_cc, dst=0, async_op=True)
-        return pending[0]
+            if pending[ln] is not None:
+                pending[ln].result()
+            pending[ln] = gather_packed(buf, counts_all, e.max_cc, dst=0, async_op=True)
+            return pending[ln]
 
-    def finish(out):
-        """(hdr, recs) of a step's return value (waits for its gather)"""
+    def finish(out, lane=0):
+        """(hdr, recs) of a step's return value (waits for its gather on the lane's stream)"""
         if world == 1:
             return out
-        return out.result()
+        with torch.cuda.stream(lanes[lane]):
+            return out.result()
+
+    def drain():
+        """all lanes: wait for the pending gathers, then make the current stream wait for the lanes"""
+        for ln in range(NL):
+            with torch.cuda.stream(lanes[ln]):
+                if pending[ln] is not None:
+                    pending[ln].result()
+                    pending[ln] = None
+            torch.cuda.current_stream().wait_stream(lanes[ln])
 
     def sync_all():
-        if pending[0] is not None:
-            pending[0].result()
-            pending[0] = None
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -271,11 +288,11 @@ def gpu_arm(args, cfg):
     n0 = _lib.launch_count()
     sync_all()
     t_start.record()
+    for ln in range(NL):
+        lanes[ln].wait_event(t_start)
     for i in range(K):
         step(i, evs[i])
-    if pending[0] is not None:          # the last gather is part of the timed region
-        pending[0].result()
-        pending[0] = None
+    drain()                             # the last gathers are part of the timed region
     t_end.record()
     sync_all()
     launches = _lib.launch_count() - n0
@@ -303,43 +320,63 @@ def gpu_arm(args, cfg):
     _lib.profile_collect()
     _lib.profile_enable(True)
     for i in range(Kp):
-        out_p = step(i)
+        out_p = step(i, lane=0)         # one lane: kernels run back to back, so each event pair times one kernel
     hdr_p, recs_p = finish(out_p)
     pending[0] = None
-    torch.cuda.synchronize()
+    sync_all()
     _lib.profile_enable(False)
     prof = {k: (ms / Kp, n // Kp) for k, (ms, n) in _lib.profile_collect().items()}   # ms per step, launches per step
     H = ops.decode_headers(hdr_p) if (rank == 0 and hdr_p is not None) else None
 
     # ---- end-to-end through the public API from pinned host buffers ---------------------------
+    # Every step copies its own inputs host->device and its records device->host inside the timed region;
+    # with NL lanes the copies of one volume overlap the kernels of the previous one, and the host waits
+    # for a volume's records before that lane's buffers are reused (and for all of them at the end).
     Ke = max(3, min(K, 50))
     h_sup = torch.from_numpy(vol.sup).pin_memory()
     h_fg = torch.from_numpy(vol.fg).pin_memory()
     h_q = [q.cpu().pin_memory() for q in qvols]
-    d_sup, d_fg, d_q = torch.empty_like(sup), torch.empty_like(fg), torch.empty_like(base)
-    hdr, recs = finish(step(0))
-    pending[0] = None
     n_img = Q * L
-    h_hdr = torch.empty((n_img, 64), dtype=torch.uint8).pin_memory()
-    h_rec = torch.empty((n_img, eng.max_cc, 96), dtype=torch.uint8).pin_memory()
+    lane_buf = []
+    for ln in range(NL):
+        with torch.cuda.stream(lanes[ln]):
+            lane_buf.append(dict(d_sup=torch.empty_like(sup), d_fg=torch.empty_like(fg), d_q=torch.empty_like(base),
+                                 h_hdr=torch.empty((n_img, 64), dtype=torch.uint8).pin_memory(),
+                                 h_rec=torch.empty((n_img, eng.max_cc, 96), dtype=torch.uint8).pin_memory(),
+                                 done=torch.cuda.Event()))
+    sync_all()
+    busy = [False] * NL
 
     def e2e_step(i):
-        d_sup.copy_(h_sup, non_blocking=True)
-        d_fg.copy_(h_fg, non_blocking=True)
-        d_q.copy_(h_q[i % N_ROTATE], non_blocking=True)
-        eng.set_support(d_sup, d_fg)
-        hd, rc = eng.run(d_q)
-        h_hdr.copy_(hd, non_blocking=True)
-        h_rec.copy_(rc, non_blocking=True)
-        torch.cuda.current_stream().synchronize()           # the caller consumes the prompts on the host
-        return ops.HDR_DTYPE, h_hdr
+        ln = i % NL
+        B, e = lane_buf[ln], engs[ln]
+        if busy[ln]:
+            B["done"].synchronize()                         # the caller consumes that volume's prompts on the host
+        with torch.cuda.stream(lanes[ln]):
+            B["d_sup"].copy_(h_sup, non_blocking=True)
+            B["d_fg"].copy_(h_fg, non_blocking=True)
+            B["d_q"].copy_(h_q[i % N_ROTATE], non_blocking=True)
+            e.set_support(B["d_sup"], B["d_fg"])
+            hd, rc = e.run(B["d_q"])
+            B["h_hdr"].copy_(hd, non_blocking=True)
+            B["h_rec"].copy_(rc, non_blocking=True)
+            B["done"].record()
+        busy[ln] = True
+
+    def e2e_drain():
+        for ln in range(NL):
+            if busy[ln]:
+                lane_buf[ln]["done"].synchronize()
+                busy[ln] = False
 
     for i in range(3):
         e2e_step(i)
+    e2e_drain()
     sync_all()
     t0 = time.perf_counter()
     for i in range(Ke):
         e2e_step(i)
+    e2e_drain()
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / Ke
     te = torch.tensor([e2e_ms], device=dev)
@@ -347,7 +384,7 @@ def gpu_arm(args, cfg):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
     h2d = h_sup.numel() * 4 + h_fg.numel() * 4 + h_q[0].numel() * 4
-    d2h = h_hdr.numel() + h_rec.numel()
+    d2h = lane_buf[0]["h_hdr"].numel() + lane_buf[0]["h_rec"].numel()
 
     if rank != 0:
         if world > 1:
@@ -440,12 +477,14 @@ def main():
     ap.add_argument("--slices", type=int, default=0, help="override query slices per GPU")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3, help="volumes in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     from protosam_b200 import synth
     cfg = dict(synth.CONFIGS[args.workload])
     cfg["name"] = args.workload
     if args.slices:
         cfg["Q"] = args.slices
+    cfg["lanes"] = args.lanes
     if args.impl == "reference":
         reference_arm(args, cfg)
     else:
