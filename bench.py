@@ -216,8 +216,11 @@ def gpu_arm(args, cfg):
     qvols = [base] + [(base.roll(k + 1, 0) + 0.05 * torch.randn(base.shape, generator=g, device=dev)).contiguous()
                       for k in range(N_ROTATE - 1)]
     NL = max(1, args.lanes)
+    # one process group (= NCCL communicator + stream) per lane: the collectives of different lanes must not
+    # queue behind each other
+    groups = [dist.new_group(list(range(world))) if world > 1 else None for _ in range(NL)]
     engs = [CoarseVolumeEngine((h, w), cfg["img_size"], out_size=1024, val_wsize=cfg["ws"], use_cca=False,
-                               point_mode="both", match_algo=args.algo) for _ in range(NL)]
+                               point_mode="both", match_algo=args.algo, group=groups[ln]) for ln in range(NL)]
     eng = engs[0]
     lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]
     q_total = Q * world
@@ -249,7 +252,7 @@ def gpu_arm(args, cfg):
                 ev[2].record()
             if pending[ln] is not None:
                 pending[ln].result()
-            pending[ln] = gather_packed(buf, counts_all, e.max_cc, dst=0, async_op=True)
+            pending[ln] = gather_packed(buf, counts_all, e.max_cc, dst=0, group=groups[ln], async_op=True)
             return pending[ln]
 
     def finish(out, lane=0):
@@ -290,8 +293,10 @@ def gpu_arm(args, cfg):
     t_start.record()
     for ln in range(NL):
         lanes[ln].wait_event(t_start)
+    th0 = time.perf_counter()
     for i in range(K):
         step(i, evs[i])
+    host_ms = (time.perf_counter() - th0) * 1e3 / K     # host time to enqueue one step (launch-bound if ~ ms_per_step)
     drain()                             # the last gathers are part of the timed region
     t_end.record()
     sync_all()
@@ -460,7 +465,7 @@ def gpu_arm(args, cfg):
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": q_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "host_enqueue_ms_per_step": host_ms,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
