@@ -192,7 +192,7 @@ def gpu_arm(args, cfg):
     import torch.distributed as dist
 
     from protosam_b200 import _lib, ops, synth
-    from protosam_b200.engine import CoarseVolumeEngine, gather_packed, shard_range
+    from protosam_b200.engine import CoarseVolumeEngine, GraphedVolumeStep, gather_packed, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,8 +226,18 @@ def gpu_arm(args, cfg):
     q_total = Q * world
     counts_all = [(b - a) * L for a, b in (shard_range(q_total, world, r) for r in range(world))]
     pending = [None] * NL
+    replayed = [0]          # library kernels launched through graph replays
+    # CUDA graphs: one per (lane, resident volume); volume i goes to lane i % NL, graph (i // NL) % len(graphs[lane])
+    graphs = None
+    if not args.no_graphs:
+        graphs = []
+        for ln in range(NL):
+            with torch.cuda.stream(lanes[ln]):
+                mine = [qvols[j] for j in range(N_ROTATE) if j % NL == ln] or [qvols[ln % N_ROTATE]]
+                graphs.append([GraphedVolumeStep(engs[ln], sup, fg, qv, q_total=q_total) for qv in mine])
+        torch.cuda.synchronize()
 
-    def step(i, ev=None, lane=None):
+    def step(i, ev=None, lane=None, eager=False):
         """One volume: prototypes (+ broadcast), match, prompts, record gather, all on the stream of lane
         i % NL: consecutive volumes are in flight on different streams, so the small launches, the collectives
         and the tail of one volume overlap the big kernels of the next.  The gather of a volume is asynchronous
@@ -235,6 +245,19 @@ def gpu_arm(args, cfg):
         ln = i % NL if lane is None else lane
         e = engs[ln]
         with torch.cuda.stream(lanes[ln]):
+            if pending[ln] is not None:
+                pending[ln].wait()
+            if graphs is not None and not eager:
+                gs = graphs[ln][(i // NL) % len(graphs[ln])]
+                if ev is not None:
+                    ev[0].record()
+                out = gs.launch()
+                replayed[0] += gs.n_kernels
+                if ev is not None:
+                    ev[2].record()
+                if world > 1:
+                    pending[ln] = out
+                return out
             e.set_support(sup, fg)
             qv = qvols[i % N_ROTATE]
             if ev is not None:
@@ -250,8 +273,6 @@ def gpu_arm(args, cfg):
             _, _, buf = e.prompts_from_logits(logits, n_alloc=max(counts_all), return_packed=True)
             if ev is not None:
                 ev[2].record()
-            if pending[ln] is not None:
-                pending[ln].result()
             pending[ln] = gather_packed(buf, counts_all, e.max_cc, dst=0, group=groups[ln], async_op=True)
             return pending[ln]
 
@@ -267,7 +288,7 @@ def gpu_arm(args, cfg):
         for ln in range(NL):
             with torch.cuda.stream(lanes[ln]):
                 if pending[ln] is not None:
-                    pending[ln].result()
+                    pending[ln].wait()
                     pending[ln] = None
             torch.cuda.current_stream().wait_stream(lanes[ln])
 
@@ -289,6 +310,7 @@ def gpu_arm(args, cfg):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = _lib.launch_count()
+    replayed[0] = 0
     sync_all()
     t_start.record()
     for ln in range(NL):
@@ -300,14 +322,18 @@ def gpu_arm(args, cfg):
     drain()                             # the last gathers are part of the timed region
     t_end.record()
     sync_all()
-    launches = _lib.launch_count() - n0
+    launches = _lib.launch_count() - n0 + replayed[0]
     ms_total = t_start.elapsed_time(t_end)
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / K
-    ms_match = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    ms_prompt = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    if graphs is None:
+        ms_match = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+        ms_prompt = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    else:           # graph replays: only the whole volume is bracketed (the per-kernel pass below splits it)
+        ms_match = ms_prompt = None
+        ms_volume = float(np.mean([e[0].elapsed_time(e[2]) for e in evs]))
     # keep the same kernels running briefly if the timed region was too short for clock samples (rank-local work
     # only: no collective may be entered by a subset of the ranks)
     if rank == 0 and sampler.mark() - line0 < 3:
@@ -325,7 +351,7 @@ def gpu_arm(args, cfg):
     _lib.profile_collect()
     _lib.profile_enable(True)
     for i in range(Kp):
-        out_p = step(i, lane=0)         # one lane: kernels run back to back, so each event pair times one kernel
+        out_p = step(i, lane=0, eager=True)   # one lane, no graph replay: kernels run back to back, so each event pair times one kernel
     hdr_p, recs_p = finish(out_p)
     pending[0] = None
     sync_all()
@@ -351,6 +377,15 @@ def gpu_arm(args, cfg):
                                  done=torch.cuda.Event()))
     sync_all()
     busy = [False] * NL
+    e2e_graphs = None
+    if graphs is not None:
+        e2e_graphs = []
+        for ln in range(NL):
+            with torch.cuda.stream(lanes[ln]):
+                B = lane_buf[ln]
+                B["d_sup"].copy_(sup); B["d_fg"].copy_(fg); B["d_q"].copy_(base)
+                e2e_graphs.append(GraphedVolumeStep(engs[ln], B["d_sup"], B["d_fg"], B["d_q"], q_total=q_total))
+        sync_all()
 
     def e2e_step(i):
         ln = i % NL
@@ -361,8 +396,11 @@ def gpu_arm(args, cfg):
             B["d_sup"].copy_(h_sup, non_blocking=True)
             B["d_fg"].copy_(h_fg, non_blocking=True)
             B["d_q"].copy_(h_q[i % N_ROTATE], non_blocking=True)
-            e.set_support(B["d_sup"], B["d_fg"])
-            hd, rc = e.run(B["d_q"])
+            if e2e_graphs is not None:
+                hd, rc = e2e_graphs[ln].launch(gather=False)
+            else:
+                e.set_support(B["d_sup"], B["d_fg"])
+                hd, rc = e.run(B["d_q"])
             B["h_hdr"].copy_(hd, non_blocking=True)
             B["h_rec"].copy_(rc, non_blocking=True)
             B["done"].record()
@@ -439,7 +477,8 @@ def gpu_arm(args, cfg):
             "share_of_step": ms_dom / sum(v[0] for v in prof.values()) if prof else None,
             "algorithmic_work_per_launch": work, "work_model": note, "sum_prototypes": sumP,
             "kernels_ms_per_step": {k: round(v[0], 5) for k, v in prof.items()},
-            "match_stage_ms": ms_match, "prompt_stage_ms": ms_prompt}
+            "match_stage_ms": ms_match, "prompt_stage_ms": ms_prompt,
+            "volume_latency_ms": ms_volume if graphs is not None else None}
     if dom != "k_match_tc" and "k_match_tc" in prof:
         t = prof["k_match_tc"][0] * 1e-3
         roof["match_kernel"] = {"kernel": "k_match_tc", "bound": "tensor", "achieved": flops_match / t / 1e12,
@@ -482,6 +521,7 @@ def main():
     ap.add_argument("--slices", type=int, default=0, help="override query slices per GPU")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from Python instead of CUDA graphs")
     ap.add_argument("--lanes", type=int, default=3, help="volumes in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     from protosam_b200 import synth

@@ -532,14 +532,16 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
                                                        scale);
     PSAM_CHECK_LAUNCH("k_pack_query");
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {       // once per device
         cudaError_t e = cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("k_match_tc: cudaFuncSetAttribute(%d bytes): %s", SMEM_BYTES, cudaGetErrorString(e));
             return PSAM_ERR_LAUNCH;
         }
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int sms = sm_count();
     int nsplit = (4 * sms + L.ntiles - 1) / L.ntiles;

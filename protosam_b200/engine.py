@@ -65,12 +65,16 @@ class PendingGather:
         p._ready = pair
         return p
 
-    def result(self):
-        if self._ready is not None:
-            return self._ready
+    def wait(self):
+        """make the current stream wait for the gather (no host block, no re-packing)"""
         if self.work is not None:
             self.work.wait()
             self.work = None
+
+    def result(self):
+        if self._ready is not None:
+            return self._ready
+        self.wait()
         if self.bucket is None:
             return None, None
         parts = [ops.split_records(b, self.max_cc) for b in self.bucket]
@@ -82,7 +86,7 @@ def gather_packed(buf: torch.Tensor, counts: Sequence[int], max_cc: int, dst: in
                   async_op: bool = False):
     """ONE gather of the per-rank packed (headers | records) buffers, all sized for max(counts) images."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    bucket = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    bucket = list(torch.empty((world, buf.numel()), dtype=buf.dtype, device=buf.device).unbind(0)) if rank == dst else None
     work = dist.gather(buf, bucket, dst=dst, group=group, async_op=async_op)
     pend = PendingGather(work if async_op else None, bucket, list(counts), max_cc, buf)
     return pend if async_op else pend.result()
@@ -127,7 +131,7 @@ class CoarseVolumeEngine:
         return 1, 0
 
     # -- support side ----------------------------------------------------------------------------
-    def set_support(self, sup_feats: torch.Tensor, fg_masks: torch.Tensor, src: int = 0):
+    def set_support(self, sup_feats: torch.Tensor, fg_masks: torch.Tensor, src: int = 0, broadcast: bool = True):
         """sup_feats [S,h,w,C] channels-last support features (S = 1, the reference's n_shots);
         fg_masks [L,S,h,w] foreground masks at feature resolution (nearest-downsampled like
         grid_proto_fewshot.py:228-231).  Computes on `src`, broadcasts to the other ranks."""
@@ -151,7 +155,9 @@ class CoarseVolumeEngine:
             N = S * gh * gw
             protos = ops.proto_table_alloc(2 * L, N + S, C, sup_feats.device)
             protos.update(N=N, gh=gh, gw=gw, S=S, C=C)
-        self.protos = broadcast_prototypes(protos, src=src, group=self.group)
+        self.protos = protos
+        if broadcast:
+            broadcast_prototypes(protos, src=src, group=self.group)
         return self.protos
 
     # -- query side ------------------------------------------------------------------------------
@@ -192,3 +198,60 @@ class CoarseVolumeEngine:
         L = self.n_labels
         flat = [P.prompts_from_records(H[i], R[i], self.use_cca, self.point_mode) for i in range(len(H))]
         return [flat[q * L:(q + 1) * L] for q in range(len(flat) // L)]
+
+
+class GraphedVolumeStep:
+    """One volume's device work captured into CUDA graphs for fixed input buffers, so that a step costs the host
+    two graph launches and two collectives instead of ~20 Python-level launches (the path is launch-bound on the
+    host once several ranks share the host's cores):
+
+        graph 1 (rank `src` only)  kernel 1 over the support slice -> prototype table
+        broadcast                  of the table (one NCCL call, outside the graphs)
+        graph 2                    kernel 2 + kernels 3a/3b over this rank's query slices -> packed records
+        gather                     of the packed records (one NCCL call, asynchronous)
+
+    `sup_feats`, `fg_masks`, `qry_local` are the buffers the graphs read: refill them in place (or copy new data
+    into them on the same stream) before each `launch()`.
+    """
+
+    def __init__(self, eng: CoarseVolumeEngine, sup_feats: torch.Tensor, fg_masks: torch.Tensor,
+                 qry_local: torch.Tensor, q_total: Optional[int] = None, src: int = 0, dst: int = 0):
+        self.eng, self.src, self.dst = eng, src, dst
+        world, rank = eng._world()
+        self.world, self.rank = world, rank
+        L = fg_masks.shape[0]
+        q_total = q_total if q_total is not None else qry_local.shape[0] * world
+        self.counts = [(hi - lo) * L for lo, hi in (shard_range(q_total, world, r) for r in range(world))]
+        n_alloc = max(self.counts)
+        # eager warm-up on the current stream: sizes workspaces, sets kernel attributes, primes the allocator
+        eng.set_support(sup_feats, fg_masks, src=src)
+        eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc, return_packed=True)
+        torch.cuda.current_stream().synchronize()
+        self.g1 = None
+        k0 = ops._lib.launch_count()
+        if world == 1 or rank == src:
+            self.g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g1):
+                eng.set_support(sup_feats, fg_masks, src=src, broadcast=False)
+        else:
+            eng.set_support(sup_feats, fg_masks, src=src, broadcast=False)     # allocates the receive table
+        self.protos = eng.protos
+        self.g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g2):
+            self.hdr, self.recs, self.buf = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc,
+                                                                    return_packed=True)
+        self.n_kernels = int(ops._lib.launch_count() - k0)      # library kernels one launch() replays
+
+    def launch(self, async_gather: bool = True, gather: bool = True):
+        """Enqueue one volume on the current stream.  -> this rank's (hdr, recs) device views when world == 1 or
+        gather is False, else a PendingGather (or the gathered pair when async_gather is False)."""
+        if self.g1 is not None:
+            self.g1.replay()
+        if self.world > 1:
+            broadcast_prototypes(self.protos, src=self.src, group=self.eng.group)
+        self.g2.replay()
+        if self.world == 1 or not gather:
+            n = self.counts[self.rank]
+            return self.hdr[:n], self.recs[:n]
+        return gather_packed(self.buf, self.counts, self.eng.max_cc, dst=self.dst, group=self.eng.group,
+                             async_op=async_gather)
