@@ -113,7 +113,8 @@ int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, int vw, floa
  *   assign     [Q,nsets,HW] or NULL: argmax_p d as float (grid modes) / the score (mask mode).
  *   sims       [Q,nsets,cap_rows,HW] or NULL: raw d ('raw_local_sims', vis_sim=True).
  *   status     [nsets] int32, PSAM_SET_EMPTY is OR-ed in for empty grid sets.
- *   algo       0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 split-bf16 tensor-core kernel.
+ *   algo       0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 split-bf16 tensor-core kernel fed from packed
+ *              operand images, 3 = the same GEMM with the fp32 -> bf16 hi/lo conversion of the query fused into it.
  * ------------------------------------------------------------------------------------ */
 size_t psam_alp_match_workspace(int Q, int HW, int C, int nsets, int cap_rows, int algo);
 

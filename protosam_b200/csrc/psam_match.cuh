@@ -25,7 +25,8 @@ int launch_match_simt(const MatchParams& p, cudaStream_t stream);
 
 // tcgen05 tensor-core variant (psam_match_tc.cu)
 bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want_sims);
-size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows);
-int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// fused = the GEMM converts the fp32 query rows itself (no packed query image, no separate pass over the query)
+size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fused);
+int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, bool fused, cudaStream_t stream);
 
 }  // namespace psam

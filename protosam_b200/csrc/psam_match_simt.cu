@@ -22,6 +22,11 @@
 
 #include "psam_match.cuh"
 
+// which tensor-core variant algo = 0 (auto) takes
+#ifndef PSAM_AUTO_FUSED
+#define PSAM_AUTO_FUSED 0
+#endif
+
 namespace psam {
 
 constexpr int BM = 128, BN = 64, BK = 16, APAD = 4;
@@ -197,10 +202,11 @@ using namespace psam;
 
 extern "C" size_t psam_alp_match_workspace(int Q, int HW, int C, int nsets, int cap_rows, int algo)
 {
-    // algo 1 needs no scratch; 0 (auto) and 2 may run the tensor-core variant, which stages bf16 operand images
+    // algo 1 needs no scratch; 2 / 3 stage bf16 operand images (3 = fused: of the prototypes only); 0 (auto) may run
+    // either tensor-core variant, so it asks for the larger one
     if (algo == 1 || Q < 1 || HW < 1 || C < 1 || nsets < 1 || cap_rows < 1) return 256;
     if (!match_tc_supported(Q, HW, C, nsets, cap_rows, false)) return 256;
-    return match_tc_workspace(Q, HW, C, nsets, cap_rows);
+    return match_tc_workspace(Q, HW, C, nsets, cap_rows, algo == 3);
 }
 
 extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t row_stride, int Q, int HW, int C,
@@ -216,14 +222,17 @@ extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t ro
                    "psam_alp_match: C, row_stride and slice_stride must be multiples of 4 floats (16-byte rows)");
     PSAM_CHECK_ARG((reinterpret_cast<uintptr_t>(qry) & 15) == 0 && (reinterpret_cast<uintptr_t>(protos) & 15) == 0,
                    "psam_alp_match: qry/protos must be 16-byte aligned");
-    PSAM_CHECK_ARG(algo >= 0 && algo <= 2, "psam_alp_match: algo %d", algo);
+    PSAM_CHECK_ARG(algo >= 0 && algo <= 3, "psam_alp_match: algo %d", algo);
     MatchParams p{qry, slice_stride, row_stride, Q, HW, C, protos, cap_rows, counts, eff_modes,
                   nsets, scores, assign, sims, status};
-    if (algo == 2) return launch_match_tc(p, workspace, workspace_bytes, stream);
+    if (algo == 2 || algo == 3) return launch_match_tc(p, workspace, workspace_bytes, algo == 3, stream);
     // auto: tensor cores whenever the variant applies (the raw-similarity dump for visualisation and channel
     // counts that are not a multiple of 8 stay on the CUDA-core kernel) and the caller sized the workspace for it
-    if (algo == 0 && match_tc_supported(Q, HW, C, nsets, cap_rows, sims != nullptr) && workspace &&
-        workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows))
-        return launch_match_tc(p, workspace, workspace_bytes, stream);
+    if (algo == 0 && match_tc_supported(Q, HW, C, nsets, cap_rows, sims != nullptr) && workspace) {
+        if (PSAM_AUTO_FUSED && workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, true))
+            return launch_match_tc(p, workspace, workspace_bytes, true, stream);
+        if (workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, false))
+            return launch_match_tc(p, workspace, workspace_bytes, false, stream);
+    }
     return launch_match_simt(p, stream);
 }

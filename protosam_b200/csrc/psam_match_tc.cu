@@ -57,6 +57,8 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for the 1024
 constexpr int MAX_SETS = 128;
 constexpr int MAX_SPLIT = 8;
 constexpr int THREADS = 192;
+constexpr int CONV_WARPS = 8;                    // fused variant: warps 6..13 convert the query tile
+constexpr int THREADS_FUSED = THREADS + CONV_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -257,6 +259,10 @@ struct TcParams {
     float* assign;
     int32_t* status;
     int nsets, HW, R, ntiles, KB, G, nsplit;
+    // fused variant: the query rows themselves (fp32, channels-last)
+    const float* qry;
+    int64_t slice_stride, row_stride;
+    int C;
 };
 
 struct RowAcc {
@@ -279,10 +285,17 @@ __device__ __forceinline__ void fold16(const float (&v)[16], int nvalid, int nba
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
+// kFused = false: both operands arrive as pre-packed images through the TMA engine (k_pack_query ran before).
+// kFused = true : 8 extra "converter" warps read the fp32 query rows of the tile straight from global memory,
+//                 split them into bf16 hi/lo, store them swizzled into the A stage (generic proxy ->
+//                 fence.proxy.async -> mbarrier), and accumulate the row norms on the way: the query is read from
+//                 HBM exactly once by the whole path and no operand image of it is ever written.
+template <bool kFused>
+__global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_tc(const TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2];
+    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2], s_scale_full[2];
+    __shared__ float s_scale[2][BM];
     __shared__ uint32_t s_tmem;
     __shared__ int s_count[MAX_SETS];
     __shared__ int s_split_set[MAX_SPLIT + 1], s_split_col[MAX_SPLIT + 1];
@@ -312,8 +325,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
         for (; k < p.nsplit; ++k) { s_split_set[k] = p.nsets; s_split_col[k] = T; }
         s_split_set[p.nsplit] = p.nsets;
         s_split_col[p.nsplit] = T;
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_tfull[i], 1); mbar_init(&s_tempty[i], 4); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], kFused ? 1 + CONV_WARPS : 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_tfull[i], 1);
+            mbar_init(&s_tempty[i], 4);
+            mbar_init(&s_scale_full[i], CONV_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -343,8 +360,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                         mbar_wait(&s_empty[s], ph ^ 1);
                         uint8_t* sa = smem + s * STAGE_BYTES;
-                        mbar_expect_tx(&s_full[s], A_STAGE_BYTES + bytes_b);
-                        bulk_g2s(sa, a_tile + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &s_full[s]);
+                        mbar_expect_tx(&s_full[s], (kFused ? 0 : A_STAGE_BYTES) + bytes_b);
+                        if (!kFused) bulk_g2s(sa, a_tile + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &s_full[s]);
                         bulk_g2s(sa + A_STAGE_BYTES, p.b_img + ((size_t)kb * p.G + (n0 >> 3)) * GROUP_BYTES, bytes_b,
                                  &s_full[s]);
                     }
@@ -383,19 +400,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
                 }
             }
         }
-    } else {
+    } else if (warp < 6) {
         // ===== epilogue: TMEM -> per-set reductions -> global =====
         const int lg = warp & 3;                       // TMEM lane group this warp may read
         const int row_in_tile = lg * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-        uint32_t cit = 0;
+        uint32_t cit = 0, nz = 0;
         for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
             const int split = it / p.ntiles, tile = it - split * p.ntiles;
             const int c0 = s_split_col[split];
             const int g = tile * BM + row_in_tile;
             const bool valid = g < p.R;
             const int q = valid ? g / p.HW : 0, pix = valid ? g - q * p.HW : 0;
-            const float sc = valid ? __ldg(p.scale + g) : 0.f;
+            float sc;
+            if (kFused) {
+                sc = 0.f;
+                if (c0 < s_split_col[split + 1]) {     // the converters publish the row scales of every non-empty item
+                    mbar_wait(&s_scale_full[nz & 1], (nz >> 1) & 1);
+                    sc = s_scale[nz & 1][row_in_tile];
+                    ++nz;
+                }
+            } else {
+                sc = valid ? __ldg(p.scale + g) : 0.f;
+            }
             const float sc2 = sc * LOG2E;
             int col = 0;                                // column cursor relative to c0
             int cur_chunk = -1;
@@ -452,6 +479,90 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
         }
     }
 
+    else if (kFused) {
+        // ===== converters: fp32 query rows -> bf16 hi/lo operand tile in shared memory =====
+        // lane (r = lane & 7, cq = lane >> 3) of converter warp cw owns rows cw*8 + r and 64 + cw*8 + r of the tile
+        // and the 8-channel chunks cq and cq + 4 of every 64-channel k-block: a warp reads 8 rows x 128 contiguous
+        // bytes per load instruction and writes conflict-free 16-byte chunks at their swizzled positions.
+        const int cw = warp - 6, r = lane & 7, cq = lane >> 3;
+        uint32_t kit = 0, nz = 0;
+        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+            const int split = it / p.ntiles, tile = it - split * p.ntiles;
+            const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
+            if (c0 >= c1) continue;
+            const float* src[2];
+            bool ok[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int g = tile * BM + j * 64 + cw * 8 + r;
+                ok[j] = g < p.R;
+                const int q = ok[j] ? g / p.HW : 0, pix = ok[j] ? g - q * p.HW : 0;
+                src[j] = p.qry + (size_t)q * p.slice_stride + (size_t)pix * p.row_stride;
+            }
+            float ssq[2] = {0.f, 0.f};
+            float4 cur[8], nxt[8];
+            auto gload = [&](float4 (&v)[8], int kb) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k0 = kb * BK + (cq + 4 * h) * 8;
+                        const bool in = ok[j] && k0 < p.C;
+                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[j * 4 + h * 2 + 0] = in ? __ldg(reinterpret_cast<const float4*>(src[j] + k0)) : z;
+                        v[j * 4 + h * 2 + 1] = in ? __ldg(reinterpret_cast<const float4*>(src[j] + k0 + 4)) : z;
+                    }
+            };
+            gload(cur, 0);
+            for (int n0 = c0; n0 < c1; n0 += NCH) {
+                const bool first = (n0 == c0);
+                for (int kb = 0; kb < p.KB; ++kb, ++kit) {
+                    const bool more = (kb + 1 < p.KB) || (n0 + NCH < c1);
+                    if (more) gload(nxt, kb + 1 < p.KB ? kb + 1 : 0);      // next k-block in flight while this one converts
+                    const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                    mbar_wait(&s_empty[s], ph ^ 1);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float4 x = cur[j * 4 + h * 2], y = cur[j * 4 + h * 2 + 1];
+                            const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                            if (first) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) ssq[j] = fmaf(v[i], v[i], ssq[j]);
+                            }
+                            uint4 hi, lo;
+                            split8(v, hi, lo);
+                            uint8_t* dst = sa + (j * 8 + cw) * GROUP_BYTES + r * 128 + (((cq + 4 * h) ^ r) << 4);
+                            *reinterpret_cast<uint4*>(dst) = hi;
+                            *reinterpret_cast<uint4*>(dst + 1024) = lo;
+                        }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_full[s]);
+                    if (more) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+                    }
+                }
+                if (first) {
+                    // row norms: the 4 lanes with equal r hold the partial sums of one row
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float t = ssq[j];
+                        t += __shfl_xor_sync(0xffffffffu, t, 8);
+                        t += __shfl_xor_sync(0xffffffffu, t, 16);
+                        if (cq == 0) s_scale[nz & 1][j * 64 + cw * 8 + r] = ok[j] ? 20.0f / fmaxf(sqrtf(t), 1e-4f) : 0.f;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_scale_full[nz & 1]);
+                    ++nz;
+                }
+            }
+        }
+    }
+
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -498,61 +609,69 @@ bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want
     return !want_sims && C % 8 == 0 && nsets <= tc::MAX_SETS && (long long)Q * HW < (1ll << 30);
 }
 
-size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows)
+size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fused)
 {
     const tc::Layout L = tc::make_layout(Q, HW, C, nsets, cap_rows);
+    if (fused) return align_up(L.b_bytes, 1024) + 1024;
     return align_up(L.a_bytes, 1024) + align_up(L.b_bytes, 1024) + align_up(L.scale_bytes, 1024) + 1024;
 }
 
-int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+template <bool kFused>
+static int launch_gemm(const tc::TcParams& t, int grid, cudaStream_t stream)
 {
     using namespace tc;
-    if (!match_tc_supported(p.Q, p.HW, p.C, p.nsets, p.cap_rows, p.sims != nullptr)) {
-        set_error("psam_alp_match: the tensor-core variant needs C %% 8 == 0, nsets <= %d and sims == NULL", MAX_SETS);
-        return PSAM_ERR_UNSUPPORTED;
-    }
-    if (!workspace || workspace_bytes < match_tc_workspace(p.Q, p.HW, p.C, p.nsets, p.cap_rows)) {
-        set_error("psam_alp_match: workspace too small for the tensor-core variant (%zu < %zu)", workspace_bytes,
-                  match_tc_workspace(p.Q, p.HW, p.C, p.nsets, p.cap_rows));
-        return PSAM_ERR_WORKSPACE;
-    }
-    const Layout L = make_layout(p.Q, p.HW, p.C, p.nsets, p.cap_rows);
-    uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
-    uint8_t* a_img = base;
-    uint8_t* b_img = a_img + align_up(L.a_bytes, 1024);
-    float* scale = reinterpret_cast<float*>(b_img + align_up(L.b_bytes, 1024));
-
-    PSAM_PROF_BEGIN(stream);
-
-    k_pack_protos<<<dim3(pad16(p.cap_rows) / 8, p.nsets), 256, 0, stream>>>(p.protos, p.cap_rows, p.counts, p.C, L.KB, L.G,
-                                                                           b_img);
-    PSAM_CHECK_LAUNCH("k_pack_protos");
-    PSAM_PROF_BEGIN(stream);
-    k_pack_query<<<L.ntiles * BM / 8, 256, 0, stream>>>(p.qry, p.slice_stride, p.row_stride, p.HW, L.R, p.C, L.KB, a_img,
-                                                       scale);
-    PSAM_CHECK_LAUNCH("k_pack_query");
-
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {       // once per device
-        cudaError_t e = cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_match_tc<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("k_match_tc: cudaFuncSetAttribute(%d bytes): %s", SMEM_BYTES, cudaGetErrorString(e));
             return PSAM_ERR_LAUNCH;
         }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
+    PSAM_PROF_BEGIN(stream);
+    k_match_tc<kFused><<<grid, kFused ? THREADS_FUSED : THREADS, SMEM_BYTES, stream>>>(t);
+    PSAM_CHECK_LAUNCH(kFused ? "k_match_tc_fused" : "k_match_tc");
+    return PSAM_OK;
+}
+
+int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, bool fused, cudaStream_t stream)
+{
+    using namespace tc;
+    if (!match_tc_supported(p.Q, p.HW, p.C, p.nsets, p.cap_rows, p.sims != nullptr)) {
+        set_error("psam_alp_match: the tensor-core variant needs C %% 8 == 0, nsets <= %d and sims == NULL", MAX_SETS);
+        return PSAM_ERR_UNSUPPORTED;
+    }
+    const size_t need = match_tc_workspace(p.Q, p.HW, p.C, p.nsets, p.cap_rows, fused);
+    if (!workspace || workspace_bytes < need) {
+        set_error("psam_alp_match: workspace too small for the tensor-core variant (%zu < %zu)", workspace_bytes, need);
+        return PSAM_ERR_WORKSPACE;
+    }
+    const Layout L = make_layout(p.Q, p.HW, p.C, p.nsets, p.cap_rows);
+    uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+    uint8_t* b_img = base;
+    uint8_t* a_img = fused ? nullptr : b_img + align_up(L.b_bytes, 1024);
+    float* scale = fused ? nullptr : reinterpret_cast<float*>(a_img + align_up(L.a_bytes, 1024));
+
+    PSAM_PROF_BEGIN(stream);
+    k_pack_protos<<<dim3(pad16(p.cap_rows) / 8, p.nsets), 256, 0, stream>>>(p.protos, p.cap_rows, p.counts, p.C, L.KB, L.G,
+                                                                           b_img);
+    PSAM_CHECK_LAUNCH("k_pack_protos");
+    if (!fused) {
+        PSAM_PROF_BEGIN(stream);
+        k_pack_query<<<L.ntiles * BM / 8, 256, 0, stream>>>(p.qry, p.slice_stride, p.row_stride, p.HW, L.R, p.C, L.KB,
+                                                           a_img, scale);
+        PSAM_CHECK_LAUNCH("k_pack_query");
+    }
     const int sms = sm_count();
     int nsplit = (4 * sms + L.ntiles - 1) / L.ntiles;
     nsplit = max(1, min(min(nsplit, p.nsets), MAX_SPLIT));
     TcParams t{a_img, b_img, scale, p.counts, p.eff_modes, p.scores, p.assign, p.status,
-               p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit};
+               p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit, p.qry, p.slice_stride, p.row_stride, p.C};
     const int grid = min(sms, L.ntiles * nsplit);
-    PSAM_PROF_BEGIN(stream);
-    k_match_tc<<<grid, THREADS, SMEM_BYTES, stream>>>(t);
-    PSAM_CHECK_LAUNCH("k_match_tc");
-    return PSAM_OK;
+    return fused ? launch_gemm<true>(t, grid, stream) : launch_gemm<false>(t, grid, stream);
 }
 
 }  // namespace psam
