@@ -522,7 +522,7 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from Python instead of CUDA graphs")
-    ap.add_argument("--lanes", type=int, default=3, help="volumes in flight per GPU (CUDA streams)")
+    ap.add_argument("--lanes", type=int, default=4, help="volumes in flight per GPU (CUDA streams)")
     args = ap.parse_args()
     from protosam_b200 import synth
     cfg = dict(synth.CONFIGS[args.workload])

@@ -95,6 +95,11 @@ int psam_alp_prototypes(const float* sup_x, const int64_t* sup_x_strides, const 
                         uint8_t* survive, float* pooled,
                         void* workspace, size_t workspace_bytes, psam_stream_t stream);
 
+/* Nearest-neighbour resize of the support masks to feature resolution, as FewShotSeg.forward does before calling
+ * the ALP module (F.interpolate(mask, fts_size, mode='nearest'), models/grid_proto_fewshot.py:228-231):
+ * src [n,H,W] -> dst [n,h,w], source index = min(floor(dst * (float)in / out), in - 1). */
+int psam_mask_nearest(const float* src, int n, int H, int W, int h, int w, float* dst, psam_stream_t stream);
+
 /* Viz grid returned as 4th output of MultiProtoAsConv.forward for the grid modes
  * (`resized_proto_grid`, models/alpmodule.py:120-128, 142-150) from the `pooled` values of one
  * set: out [gh*vw, gw*vw] float32 (the reference builds it on the CPU in a Python loop). */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "psam_alp_prototypes_workspace": (c_sz, [c_i] * 7),
     "psam_alp_prototypes": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "psam_mask_nearest": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "psam_alp_proto_grid": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
     "psam_alp_match_workspace": (c_sz, [c_i] * 6),
     "psam_alp_match": (c_i, [c_p, c_i64, c_i64, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p,

@@ -301,9 +301,40 @@ __global__ void __launch_bounds__(256) k_proto_grid(const float* __restrict__ po
     (void)ord;
 }
 
+// ------------------------------------------------------------------------------------
+// F.interpolate(mask, (h,w), mode='nearest') of the support masks (models/grid_proto_fewshot.py:228-231):
+// ATen's nearest index = min(floor(dst * scale), in - 1) with scale = (float)in / out.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mask_nearest(const float* __restrict__ src, int n, int H, int W, int h, int w,
+                                                      float* __restrict__ dst)
+{
+    const size_t total = (size_t)n * h * w;
+    const float sy = __fdiv_rn((float)H, (float)h), sx = __fdiv_rn((float)W, (float)w);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int x = (int)(i % w), y = (int)((i / w) % h);
+        const size_t img = i / ((size_t)w * h);
+        const int iy = min((int)floorf(__fmul_rn((float)y, sy)), H - 1);
+        const int ix = min((int)floorf(__fmul_rn((float)x, sx)), W - 1);
+        dst[i] = src[(img * H + iy) * W + ix];
+    }
+}
+
 }  // namespace psam
 
 using namespace psam;
+
+extern "C" int psam_mask_nearest(const float* src, int n, int H, int W, int h, int w, float* dst, psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(src && dst, "psam_mask_nearest: null pointer");
+    PSAM_CHECK_ARG(n >= 1 && H >= 1 && W >= 1 && h >= 1 && w >= 1, "psam_mask_nearest: bad shape");
+    const size_t total = (size_t)n * h * w;
+    const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+    PSAM_PROF_BEGIN(stream);
+    k_mask_nearest<<<grid, 256, 0, stream>>>(src, n, H, W, h, w, dst);
+    PSAM_CHECK_LAUNCH("k_mask_nearest");
+    return PSAM_OK;
+}
 
 extern "C" size_t psam_alp_prototypes_workspace(int nsets, int S, int C, int h, int w, int kh, int kw)
 {

@@ -160,6 +160,13 @@ class CoarseVolumeEngine:
             broadcast_prototypes(protos, src=src, group=self.group)
         return self.protos
 
+    def set_support_from_image_masks(self, sup_feats: torch.Tensor, fg_img_masks: torch.Tensor, src: int = 0,
+                                     broadcast: bool = True):
+        """As set_support, from masks at image resolution [L,S,H,W]: the nearest-neighbour resize to the feature
+        map that FewShotSeg.forward does first (grid_proto_fewshot.py:228-231) runs on the device too."""
+        return self.set_support(sup_feats, ops.mask_nearest(fg_img_masks.to(torch.float32), self.h, self.w), src=src,
+                                broadcast=broadcast)
+
     # -- query side ------------------------------------------------------------------------------
     def match(self, qry_feats: torch.Tensor) -> torch.Tensor:
         """qry_feats [Q,h,w,C] channels-last -> coarse logits [Q*L, 2, h, w] (bg, fg per label)."""

@@ -99,6 +99,19 @@ def alp_prototypes(sup_x, sup_y, modes, ksize, thresh, auto_ksize=None):
     return out
 
 
+def mask_nearest(masks, h, w):
+    """F.interpolate(masks, (h, w), mode='nearest') for float masks [..., H, W] (grid_proto_fewshot.py:228-231)."""
+    L = _lib.load()
+    _need_cuda(masks)
+    src = masks.contiguous()
+    H, W = src.shape[-2:]
+    n = src.numel() // (H * W)
+    dst = torch.empty(tuple(src.shape[:-2]) + (h, w), dtype=torch.float32, device=src.device)
+    rc = L.psam_mask_nearest(_ptr(src), n, H, W, int(h), int(w), _ptr(dst), _stream())
+    _lib.check(rc, "psam_mask_nearest")
+    return dst
+
+
 def alp_proto_grid(pooled_set, S, gh, gw, vw, thresh, mode):
     """`resized_proto_grid` [1,1,gh*vw,gw*vw] of one set (viz only)."""
     L = _lib.load()

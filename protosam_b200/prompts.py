@@ -84,6 +84,12 @@ def prompts_from_records(hdr: np.void, recs: np.ndarray, use_cca: bool, point_mo
                         not use_cca, flags)
 
 
+def medsam_boxes(boxes_xyxy: np.ndarray, W: int, H: int, image_size=(1024, 1024)) -> np.ndarray:
+    """ProtoMedSAM.forward's box hand-off (models/ProtoMedSAM.py:197-200): the per-component XYXY boxes of
+    get_bbox_per_cc rescaled to MedSAM's input frame, ``bbox / [W, H, W, H] * max(image_size)`` in float64."""
+    return boxes_xyxy / np.array([W, H, W, H]) * max(image_size)
+
+
 def coarse_to_prompts(low_logits: torch.Tensor, mid_size: int, out_size: int = 1024, use_cca: bool = False,
                       point_mode: str = BOTH_MODE, max_cc: int = ops.DEFAULT_MAX_CC,
                       max_runs: int = ops.DEFAULT_MAX_RUNS) -> List[SlicePrompts]:

@@ -86,3 +86,11 @@ def test_cpu_tensors_are_rejected():
     from protosam_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.upsample_softmax(torch.zeros(1, 2, 8, 8), 16, 32)
+
+
+def test_medsam_box_handoff_matches_reference_formula():
+    """models/ProtoMedSAM.py:197-200"""
+    from protosam_b200 import prompts
+    box = np.array([[10, 20, 300, 400], [0, 0, 671, 671]], np.int64)
+    out = prompts.medsam_boxes(box, 672, 672)
+    assert out.dtype == np.float64 and np.array_equal(out, box / np.array([672, 672, 672, 672]) * 1024)

@@ -485,3 +485,21 @@ def test_cfg4_polyp_mask_and_gridconv_single_stage(hw, point_mode):
         if not s.empty:
             assert np.array_equal(s.boxes, rp["bboxes"])
             assert np.array_equal(s.points, rp["points"]) and s.points.dtype == rp["points"].dtype
+
+
+def test_mask_nearest_matches_aten_and_feeds_the_engine():
+    """the caller-side nearest resize of the support masks (grid_proto_fewshot.py:228-231) on the device"""
+    for (H, hh) in ((256, 32), (518, 37), (672, 48), (1024, 73), (37, 37)):
+        m = (torch.rand((2, 1, H, H), generator=torch.Generator().manual_seed(H)) > 0.6).float()
+        ref = torch.nn.functional.interpolate(m, size=(hh, hh), mode="nearest")
+        got = ops.mask_nearest(m.to(DEV), hh, hh)
+        assert torch.equal(got.cpu(), ref)
+    cfg = synth.CONFIGS["cfg2_chaos_mri"]
+    vol = synth.make_volume(77, Q=1, L=2, C=64, h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"])
+    pa = eng.set_support_from_image_masks(_t(vol.sup), _t(vol.fg_img))
+    a, ca = pa["protos"].clone(), pa["counts"].clone()
+    pb = eng.set_support(_t(vol.sup), _t(vol.fg))
+    assert torch.equal(ca, pb["counts"])
+    for i, c in enumerate(ca.tolist()):          # rows beyond a set's count are unspecified
+        assert torch.equal(a[i, :c], pb["protos"][i, :c])
