@@ -491,7 +491,7 @@ def gpu_arm(args, cfg):
     # ---- CPU baseline: the oracle port, one core, bounded sample ---------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ns = 2
+        ns = 12                                       # ~10 s of one host core
         val, dt = run_cpu_port(cfg, ns, 1, 1, 0)
         cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{ns} query slices x {L} labels, one pass, C port of the reference path (oracle/), "

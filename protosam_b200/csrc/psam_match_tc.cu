@@ -344,6 +344,8 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    // item = (tile, split), splits of one tile adjacent: they run on neighbouring CTAs at the same time, so the
+    // second read of the tile's operand block hits L2
     const int nitems = p.ntiles * p.nsplit;
 
     if (warp == 0) {
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
         if (lane == 0) {
             uint32_t kit = 0;
             for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-                const int split = it / p.ntiles, tile = it - split * p.ntiles;
+                const int tile = it / p.nsplit, split = it - tile * p.nsplit;
                 const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
                 const uint8_t* a_tile = p.a_img + (size_t)tile * p.KB * A_STAGE_BYTES;
                 for (int n0 = c0; n0 < c1; n0 += NCH) {
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
         if (lane == 0) {
             uint32_t kit = 0, cit = 0;
             for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-                const int split = it / p.ntiles;
+                const int split = it % p.nsplit;
                 const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
                 for (int n0 = c0; n0 < c1; n0 += NCH, ++cit) {
                     const uint32_t b = cit & 1, tph = (cit >> 1) & 1;
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
         uint32_t cit = 0, nz = 0;
         for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-            const int split = it / p.ntiles, tile = it - split * p.ntiles;
+            const int tile = it / p.nsplit, split = it - tile * p.nsplit;
             const int c0 = s_split_col[split];
             const int g = tile * BM + row_in_tile;
             const bool valid = g < p.R;
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
         const int cw = warp - 6, r = lane & 7, cq = lane >> 3;
         uint32_t kit = 0, nz = 0;
         for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-            const int split = it / p.ntiles, tile = it - split * p.ntiles;
+            const int tile = it / p.nsplit, split = it - tile * p.nsplit;
             const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
             if (c0 >= c1) continue;
             const float* src[2];
