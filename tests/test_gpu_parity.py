@@ -503,3 +503,69 @@ def test_mask_nearest_matches_aten_and_feeds_the_engine():
     assert torch.equal(ca, pb["counts"])
     for i, c in enumerate(ca.tolist()):          # rows beyond a set's count are unspecified
         assert torch.equal(a[i, :c], pb["protos"][i, :c])
+
+
+# ------------------------------------------------------------------------------ degenerate inputs
+
+def test_engine_degenerate_masks_and_queries_vs_oracle():
+    """empty foreground, full foreground (empty background set), a mask smaller than any window, an all-zero query
+    pixel and an all-zero query slice: status bits, modes and maps agree with the oracle / the reference's rules"""
+    h = w = 16
+    C, img = 64, 128
+    vol = synth.make_volume(31, Q=3, L=1, C=C, h=h, w=w, img_size=img)
+    fg = np.zeros((4, 1, h, w), np.float32)
+    fg[1] = 1.0                       # label 1: everything foreground -> bg 'gridconv' set is empty
+    fg[2, 0, 3, 5] = 1.0              # label 2: one pixel -> fg decided 'mask', no local window survives
+    fg[3, 0, 4:12, 4:12] = 1.0        # label 3: a regular blob
+    qry = vol.qry.copy()
+    qry[1] = 0.0                      # all-zero slice: norms clamp at 1e-4, every similarity is exactly 0
+    qry[2, 0, 0] = 0.0                # one all-zero pixel
+    eng = CoarseVolumeEngine((h, w), img, out_size=256, val_wsize=2, proto_grid_size=8)
+    pr = eng.set_support(_t(vol.sup), _t(fg))
+    logits = eng.match(_t(qry)).cpu().numpy().reshape(3, 4, 2, h, w)
+    torch.cuda.synchronize()
+    status, eff, counts = pr["status"].cpu().numpy(), pr["eff_modes"].cpu().numpy(), pr["counts"].cpu().numpy()
+    names = [_lib.MODE_NAMES[int(e)] for e in eff]
+    # label 0: no foreground at all -> fg 'mask' with a zero prototype; bg uses every window
+    assert names[0] == "gridconv" and names[1] == "mask" and counts[0] == 64 and counts[1] == 1
+    # label 1: bg set empty -> flagged, NaN scores (the reference raises inside F.conv2d, alpmodule.py:68)
+    assert status[2] & _lib.SET_EMPTY and counts[2] == 0 and np.isnan(logits[:, 1, 0]).all()
+    assert names[3] == "gridconv+" and counts[3] == 64 + 1
+    assert names[5] == "mask" and counts[5] == 1
+    sup_x = np.transpose(vol.sup, (0, 3, 1, 2))[None, :, None]
+    for q in range(3):
+        qq = np.transpose(qry[q], (2, 0, 1))[None]
+        for l, (bg_ok, fg_mode) in enumerate([(True, "mask"), (False, "gridconv+"), (True, "mask"), (True, names[7])]):
+            if bg_ok:
+                ref, _, _, _ = O.alp_forward(qq, sup_x, (1.0 - fg[l])[None, :, None], "gridconv", 0.95, [2, 2], isval=True, val_wsize=2)
+                np.testing.assert_allclose(logits[q, l, 0], ref[0, 0], atol=MAP_TOL, rtol=0)
+            ref, _, _, _ = O.alp_forward(qq, sup_x, fg[l][None, :, None], fg_mode, 0.95, [2, 2], isval=True, val_wsize=2)
+            np.testing.assert_allclose(logits[q, l, 1], ref[0, 0], atol=MAP_TOL, rtol=0)
+    assert np.all(logits[1][~np.isnan(logits[1])] == 0.0)
+    # prompts from those maps: NaN scores can never be foreground; everything still agrees with the oracle bit for bit
+    got = eng.decode(*eng.run(_t(qry)))
+    flat = logits.reshape(12, 2, h, w)
+    for i in range(12):
+        ref = O.coarse_to_prompts(flat[i][None], img, 256, use_cca=False, point_mode="both")
+        s = got[i // 4][i % 4]
+        assert s.empty == ref["empty"], i
+        if not s.empty:
+            assert np.array_equal(s.boxes, ref["bboxes"]) and np.array_equal(s.points, ref["points"])
+
+
+def test_engine_rectangular_feature_maps_and_odd_channel_blocks():
+    """h != w and C not a multiple of 64 (one partially filled k-block) through all three kernels"""
+    h, w, C, img = 24, 40, 200, 256
+    sup = synth.layer_norm(synth.gaussian_like(5, (1, h, w, C)))
+    qry = (sup + 0.3 * synth.gaussian_like(6, (2, h, w, C))).astype(np.float32)
+    fg = np.zeros((1, 1, h, w), np.float32)
+    fg[0, 0, 6:18, 10:30] = 1.0
+    eng = CoarseVolumeEngine((h, w), img, out_size=256, val_wsize=2, proto_grid_size=8)
+    eng.set_support(_t(sup), _t(fg))
+    logits = eng.match(_t(qry)).cpu().numpy()
+    sup_x = np.transpose(sup, (0, 3, 1, 2))[None, :, None]
+    for q in range(2):
+        qq = np.transpose(qry[q], (2, 0, 1))[None]
+        for ch, (mask, mode) in enumerate(((1.0 - fg[0], "gridconv"), (fg[0], "gridconv+"))):
+            ref, _, _, _ = O.alp_forward(qq, sup_x, mask[None, :, None], mode, 0.95, [h // 8, w // 8], isval=True, val_wsize=2)
+            np.testing.assert_allclose(logits[q, ch], ref[0, 0], atol=MAP_TOL, rtol=0)
