@@ -49,7 +49,8 @@ def workload_desc(cfg, n_gpus):
         "l2_policy": f"{N_ROTATE} distinct query volumes rotate through the timed region "
                      f"({N_ROTATE * cfg['Q'] * cfg['h'] * cfg['w'] * cfg['C'] * 4 / 1e6:.0f} MB of inputs + "
                      f"{cfg['Q'] * cfg['L'] * 4.2:.0f} MB of per-step intermediates > 126 MB L2)",
-        "parallelism": f"slices sharded over {n_gpus} GPU(s); prototype broadcast + record gather",
+        "parallelism": f"slices sharded over {n_gpus} GPU(s); prototype broadcast (source rank = lane % ranks) + "
+                       "record gather to rank 0",
         "lanes": f"{cfg.get('lanes', 1)} volume(s) in flight per GPU on separate CUDA streams",
     }
 
@@ -203,6 +204,8 @@ def gpu_arm(args, cfg):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
+        if args.nccl_channels > 0:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))   # MB-sized messages: few CTAs suffice
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -218,7 +221,16 @@ def gpu_arm(args, cfg):
     NL = max(1, args.lanes)
     # one process group (= NCCL communicator + stream) per lane: the collectives of different lanes must not
     # queue behind each other
-    groups = [dist.new_group(list(range(world))) if world > 1 else None for _ in range(NL)]
+    def lane_group():
+        # high-priority NCCL stream: the small collective kernels must not queue behind the pending CTAs of the
+        # big compute kernels of other lanes (every rank would wait for the slowest one)
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            return dist.new_group(list(range(world)), pg_options=opts)
+        except Exception:
+            return dist.new_group(list(range(world)))
+    groups = [lane_group() if world > 1 else None for _ in range(NL)]
     engs = [CoarseVolumeEngine((h, w), cfg["img_size"], out_size=1024, val_wsize=cfg["ws"], use_cca=False,
                                point_mode="both", match_algo=args.algo, group=groups[ln]) for ln in range(NL)]
     eng = engs[0]
@@ -234,7 +246,7 @@ def gpu_arm(args, cfg):
         for ln in range(NL):
             with torch.cuda.stream(lanes[ln]):
                 mine = [qvols[j] for j in range(N_ROTATE) if j % NL == ln] or [qvols[ln % N_ROTATE]]
-                graphs.append([GraphedVolumeStep(engs[ln], sup, fg, qv, q_total=q_total) for qv in mine])
+                graphs.append([GraphedVolumeStep(engs[ln], sup, fg, qv, q_total=q_total, src=ln % world) for qv in mine])
         torch.cuda.synchronize()
 
     def step(i, ev=None, lane=None, eager=False):
@@ -258,7 +270,7 @@ def gpu_arm(args, cfg):
                 if world > 1:
                     pending[ln] = out
                 return out
-            e.set_support(sup, fg)
+            e.set_support(sup, fg, src=ln % world)
             qv = qvols[i % N_ROTATE]
             if ev is not None:
                 ev[0].record()
@@ -521,6 +533,9 @@ def main():
     ap.add_argument("--slices", type=int, default=0, help="override query slices per GPU")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-channels", type=int, default=2,
+                    help="cap NCCL channels (0 = NCCL's default): the collectives move a few MB, and every extra channel "
+                         "is a CTA that competes with the compute kernels for SMs (2 measured best at 4 and 8 GPUs)")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from Python instead of CUDA graphs")
     ap.add_argument("--lanes", type=int, default=4, help="volumes in flight per GPU (CUDA streams)")
     args = ap.parse_args()
