@@ -529,7 +529,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--algo", type=int, default=0, help="match kernel: 0 auto, 1 fp32 CUDA cores, 2 tcgen05")
+    ap.add_argument("--algo", type=int, default=0, help="match kernel: 0 auto, 1 fp32 CUDA cores, 2 tcgen05 (packed operands), 3 tcgen05 (fused conversion)")
     ap.add_argument("--slices", type=int, default=0, help="override query slices per GPU")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")

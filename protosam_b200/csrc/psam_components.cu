@@ -619,7 +619,10 @@ extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, cons
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return PSAM_ERR_LAUNCH; }
     }
     const int dyn = 2 * KEY_WORDS * (int)sizeof(uint32_t);
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& attr_done = attr_done_dev[cur_dev >= 0 && cur_dev < 64 ? cur_dev : 0];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PSAM_ERR_LAUNCH; }

@@ -19,13 +19,11 @@
 // lo_a*lo_b term and the rounding of lo are both ~2^-17 relative, i.e. the result is fp32-grade
 // (measured max |d - d_fp32| ~ 1e-5) at 1.5x the tensor time of a single TF32 pass.
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   k_pack_query   fp32 query rows -> per (128-row tile, 64-channel block) operand images: bf16
-//                  hi/lo planes already in the 128-byte-swizzled K-major layout the MMA reads,
-//                  plus the per-row scale 20/max(|q|,1e-4).  [round-1 layout; fusing this pass into
-//                  the GEMM producer is the next step, see DESIGN.md]
-//   k_pack_protos  the same for the prototype rows of all sets, concatenated (each set padded to
-//                  16 columns) so one B matrix serves every set.
+// Structure (one persistent CTA per SM):
+//   k_pack_protos  prototype rows of all sets, concatenated (each set padded to 16 columns) so one B matrix serves
+//                  every set -> bf16 hi/lo planes already in the 128-byte-swizzled K-major layout the MMA reads.
+//   k_pack_query   [algo 2] the same for the query rows, per (128-row tile, 64-channel block), plus the per-row
+//                  scale 20/max(|q|,1e-4).
 //   k_match_tc     warp 0: one thread streams operand blocks global -> shared with cp.async.bulk
 //                  (TMA engine, mbarrier complete_tx) through a 2-stage ring;
 //                  warp 1: one thread issues tcgen05.mma (M=128, N<=256, K=16, 12 per k-block)
@@ -33,6 +31,8 @@
 //                  warps 2-5: epilogue -- tcgen05.ld 16 columns at a time, scale, exp2, running
 //                  sum(e), sum(e*d), max/argmax per set, store one float per (row, set).
 //                  MMA of chunk i+1 overlaps the epilogue of chunk i.
+//                  [algo 3, kFused] warps 6-13 convert the fp32 query tile to bf16 hi/lo inside the kernel instead
+//                  of k_pack_query; correct, but slower at the named shapes (profiles/README.md), so algo 0 = algo 2.
 //
 // Roofline: tensor-bound.  Algorithmic flops per (slice, set) = 2*HW*C*P (executed: 3x that in
 // bf16).  Algorithmic bytes: SURVEY.md section 8(d).
