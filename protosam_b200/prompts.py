@@ -163,6 +163,22 @@ def get_bbox_per_cc(conn_components: ConnectedComponents) -> np.ndarray:
     return conn_components.records["box"].astype(np.int64).copy()
 
 
+def get_most_conf_points(conn_components: ConnectedComponents, cc_id: int, k: int = 1):
+    """models/ProtoSAM.py:266-289 for one component: ``(locations int64 [k,2] in (x, y), [confidences])``.
+    The reference masks the 1024^2 probability map on the host and calls torch.topk; here kernel 3b already found,
+    per component, the highest p_fg with torch.topk's tie rule (first pixel in raster order), so the answer is read
+    off the component's record.  Production uses k = num_points_for_sam = 1 (validation_protosam.py:226); k > 1
+    would need the full map on the host and is rejected rather than approximated."""
+    if k != 1:
+        raise NotImplementedError("only the reference's production setting k = 1 is computed on the device")
+    recs = conn_components.records
+    hit = np.nonzero(recs["label"] == cc_id)[0]
+    if len(hit) == 0:
+        return None, None
+    r = recs[hit[0]]
+    return r["conf_pt"].astype(np.int64)[None, :].copy(), [float(r["conf_pt_p"])]
+
+
 def get_sam_input_points(conn_components: ConnectedComponents, output_p=None, get_neg_points=False, l=1,
                          point_mode=BOTH_MODE):
     """models/ProtoSAM.py:349-450 (num_points_for_sam = 1, get_neg_points=False)."""

@@ -269,6 +269,14 @@ def test_function_level_dropins_match_oracle():
         pts, labels, _, _ = PR.get_sam_input_points(cc, None, point_mode=pm)
         rpts, rlabels = O.get_sam_input_points(rcc, p[0, 1], pm)
         assert pts.dtype == rpts.dtype and np.array_equal(pts, rpts) and np.array_equal(labels, rlabels)
+    # get_most_conf_points per component == torch.topk(p_fg[labels == j], 1) of the reference
+    import torch as _torch
+    for j in range(1, cc[0]):
+        loc, conf_j = PR.get_most_conf_points(cc, j, 1)
+        m = _torch.from_numpy(rcc[1] == j)
+        v, i = _torch.topk(_torch.from_numpy(p[0, 1])[m], 1)
+        ref_loc = _torch.nonzero(m)[i][:, [1, 0]].numpy()
+        assert np.array_equal(loc, ref_loc) and conf_j[0] == float(v[0])
     sel = PR.cca(pred, _t(lg), return_cc=True)
     rsel = O.cca(pred, p[0, 1], return_cc=True)
     assert sel[0] == rsel[0] and np.array_equal(sel[1], rsel[1]) and np.array_equal(sel[3], rsel[3])
