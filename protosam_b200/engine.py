@@ -262,3 +262,79 @@ class GraphedVolumeStep:
             return self.hdr[:n], self.recs[:n]
         return gather_packed(self.buf, self.counts, self.eng.max_cc, dst=self.dst, group=self.eng.group,
                              async_op=async_gather)
+
+
+# ---------------------------------------------------------------------------------------------
+# Support-part management of the CT/MRI protocol
+# ---------------------------------------------------------------------------------------------
+
+def part_assign(z_id: int, z_min: int, z_max: int, npart: int) -> int:
+    """Which support slice a query slice uses (dataloaders/common.py:241-249): the label's z-extent
+    [z_min, z_max] is cut into `npart` equal parts; a degenerate extent maps to part 0."""
+    try:
+        p = int((z_id - z_min) // ((z_max - z_min) / npart))
+    except ZeroDivisionError:
+        p = 0
+    return min(max(p, 0), npart - 1)
+
+
+class PartedVolumeEngine:
+    """The per-slice loop of validation_protosam.py:352-388 for one scan, batched: every label has `npart`
+    support slices (one per part of its z-extent, dataloaders/common.py:228-252) and a query slice is matched,
+    per label, against the support slice of the part it falls in.
+
+    Kernel 1 runs once per part; the z-axis is then cut at every part boundary of every label, so that inside a
+    segment each label has one fixed part and the whole segment goes through kernels 2-3 in one call with the
+    prototype sets of those parts.  Results come back in slice order."""
+
+    def __init__(self, engine: CoarseVolumeEngine, npart: int = 3):
+        self.eng, self.npart = engine, int(npart)
+        self.tables: List[dict] = []
+        self.n_labels = 0
+
+    def set_support(self, sup_feats: torch.Tensor, fg_masks: torch.Tensor):
+        """sup_feats [npart,h,w,C]: the support slice of each part; fg_masks [L,npart,h,w]."""
+        assert sup_feats.shape[0] == self.npart and fg_masks.shape[1] == self.npart
+        self.n_labels = fg_masks.shape[0]
+        self.tables = []
+        for p in range(self.npart):
+            self.eng.set_support(sup_feats[p:p + 1], fg_masks[:, p:p + 1].contiguous(), broadcast=False)
+            self.tables.append(self.eng.protos)
+        return self.tables
+
+    def _table_for(self, parts: Sequence[int]) -> dict:
+        """prototype table whose sets (bg_l, fg_l) come from part parts[l] (device-side row copies only)"""
+        t0 = self.tables[0]
+        L, cap, C = self.n_labels, t0["cap_rows"], t0["protos"].shape[2]
+        out = ops.proto_table_alloc(2 * L, cap, C, t0["protos"].device)
+        for l, p in enumerate(parts):
+            src = self.tables[p]
+            for k in ("protos", "counts", "eff_modes", "status"):
+                out[k][2 * l: 2 * l + 2].copy_(src[k][2 * l: 2 * l + 2])
+        return out
+
+    def run(self, qry_feats: torch.Tensor, z_ids: Sequence[int], z_ranges: Sequence[Tuple[int, int]],
+            return_logits: bool = False):
+        """qry_feats [Q,h,w,C] with slice indices z_ids (ascending); z_ranges[l] = (z_min, z_max) of label l.
+        -> (hdr [Q*L,64], recs [Q*L,max_cc,96]) on the device, image index = q*L + l, plus the part table
+        [Q][L] that was used (and the coarse logits [Q*L,2,h,w] when asked for)."""
+        Q, L = qry_feats.shape[0], self.n_labels
+        assert len(z_ids) == Q and len(z_ranges) == L
+        parts = [[part_assign(int(z), int(a), int(b), self.npart) for (a, b) in z_ranges] for z in z_ids]
+        hdrs, recs, logits = [], [], []
+        q0 = 0
+        while q0 < Q:                                     # maximal runs of slices with identical part vectors
+            q1 = q0 + 1
+            while q1 < Q and parts[q1] == parts[q0]:
+                q1 += 1
+            self.eng.protos = self._table_for(parts[q0])
+            self.eng.n_labels = L
+            lg = self.eng.match(qry_feats[q0:q1])
+            h, r = self.eng.prompts_from_logits(lg)
+            hdrs.append(h)
+            recs.append(r)
+            if return_logits:
+                logits.append(lg)
+            q0 = q1
+        out = (torch.cat(hdrs, 0), torch.cat(recs, 0), parts)
+        return out + (torch.cat(logits, 0),) if return_logits else out

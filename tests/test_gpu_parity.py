@@ -577,3 +577,39 @@ def test_engine_rectangular_feature_maps_and_odd_channel_blocks():
         for ch, (mask, mode) in enumerate(((1.0 - fg[0], "gridconv"), (fg[0], "gridconv+"))):
             ref, _, _, _ = O.alp_forward(qq, sup_x, mask[None, :, None], mode, 0.95, [h // 8, w // 8], isval=True, val_wsize=2)
             np.testing.assert_allclose(logits[q, ch], ref[0, 0], atol=MAP_TOL, rtol=0)
+
+
+def test_parted_volume_engine_vs_oracle_per_slice():
+    """support-part protocol (dataloaders/common.py:228-252 + validation_protosam.py:352-388): every (slice, label)
+    must equal the oracle run with the support slice of the part that slice falls in"""
+    from protosam_b200.engine import PartedVolumeEngine, part_assign
+    assert [part_assign(z, 10, 40, 3) for z in (5, 10, 19, 20, 29, 30, 40, 50)] == [0, 0, 0, 1, 1, 2, 2, 2]
+    assert part_assign(7, 7, 7, 3) == 0
+    h = w = 16
+    C, img, L, npart, Q = 64, 128, 2, 3, 7
+    sups = [synth.make_volume(60 + p, Q=1, L=L, C=C, h=h, w=w, img_size=img) for p in range(npart)]
+    sup = np.concatenate([v.sup for v in sups], 0)                               # [npart,h,w,C]
+    fg = np.stack([np.concatenate([v.fg[l] for v in sups], 0) for l in range(L)])  # [L,npart,h,w]
+    qv = synth.make_volume(99, Q=Q, L=L, C=C, h=h, w=w, img_size=img)
+    z_ids = [3, 8, 11, 14, 20, 27, 33]
+    z_ranges = [(5, 29), (10, 33)]
+    pe = PartedVolumeEngine(CoarseVolumeEngine((h, w), img, out_size=256, val_wsize=2, fg_mode="gridconv+"), npart)
+    pe.set_support(_t(sup), _t(fg))
+    hdr, recs, parts, logits = pe.run(_t(qv.qry), z_ids, z_ranges, return_logits=True)
+    logits = logits.cpu().numpy()
+    assert parts == [[part_assign(z, a, b, npart) for (a, b) in z_ranges] for z in z_ids]
+    assert len({tuple(p) for p in parts}) >= 4                                    # several segments exercised
+    got = pe.eng.decode(hdr, recs)
+    for q in range(Q):
+        qq = np.transpose(qv.qry[q], (2, 0, 1))[None]
+        for l in range(L):
+            p = parts[q][l]
+            sx = np.transpose(sup[p:p + 1], (0, 3, 1, 2))[None, :, None]
+            bg, _, _, _ = O.alp_forward(qq, sx, (1.0 - fg[l, p])[None, None, None], "gridconv", 0.95, [2, 2], isval=True, val_wsize=2)
+            fgm, _, _, _ = O.alp_forward(qq, sx, fg[l, p][None, None, None], "gridconv+", 0.95, [2, 2], isval=True, val_wsize=2)
+            np.testing.assert_allclose(logits[q * L + l], np.concatenate([bg, fgm], 1)[0], atol=MAP_TOL, rtol=0)
+            ref = O.coarse_to_prompts(logits[q * L + l][None], img, 256, use_cca=False, point_mode="both")
+            s = got[q][l]
+            assert s.empty == ref["empty"]
+            if not s.empty:
+                assert np.array_equal(s.boxes, ref["bboxes"]) and np.array_equal(s.points, ref["points"])
