@@ -613,3 +613,33 @@ def test_parted_volume_engine_vs_oracle_per_slice():
             assert s.empty == ref["empty"]
             if not s.empty:
                 assert np.array_equal(s.boxes, ref["bboxes"]) and np.array_equal(s.points, ref["points"])
+
+
+def test_graphed_volume_step_replays_equal_eager_run():
+    """CUDA-graph replay of a volume (engine.GraphedVolumeStep) == the eager engine, bit for bit, also after the
+    input buffers were refilled in place"""
+    from protosam_b200.engine import GraphedVolumeStep
+    cfg = synth.CONFIGS["cfg2_chaos_mri"]
+    vol = synth.make_volume(5, Q=3, L=2, C=128, h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    vol2 = synth.make_volume(6, Q=3, L=2, C=128, h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"])
+    sup, fg, qry = _t(vol.sup), _t(vol.fg), _t(vol.qry)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        gs = GraphedVolumeStep(eng, sup, fg, qry)
+        assert gs.n_kernels == 4 + 3 + 3            # kernel 1 (4 launches), pack x2 + GEMM, classify + exact + components
+        h1, r1 = gs.launch()
+        h1, r1 = h1.clone(), r1.clone()
+        sup.copy_(_t(vol2.sup)); fg.copy_(_t(vol2.fg)); qry.copy_(_t(vol2.qry))
+        h2, r2 = gs.launch()
+        h2, r2 = h2.clone(), r2.clone()
+    s.synchronize()
+    for v, (h, r) in ((vol, (h1, r1)), (vol2, (h2, r2))):
+        e2 = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"])
+        e2.set_support(_t(v.sup), _t(v.fg))
+        he, re_ = e2.run(_t(v.qry))
+        assert torch.equal(h, he) and torch.equal(r, re_)
+    # world == 1: run_sharded degenerates to run, also with an asynchronous handle
+    e2.set_support(_t(vol.sup), _t(vol.fg))
+    ha, ra = e2.run_sharded(_t(vol.qry), 3, async_op=True).result()
+    assert torch.equal(ha, h1) and torch.equal(ra, r1)
