@@ -36,6 +36,8 @@
 //
 // Roofline: tensor-bound.  Algorithmic flops per (slice, set) = 2*HW*C*P (executed: 3x that in
 // bf16).  Algorithmic bytes: SURVEY.md section 8(d).
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -670,6 +672,10 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     const int sms = sm_count();
     int nsplit = (4 * sms + L.ntiles - 1) / L.ntiles;
     nsplit = max(1, min(min(nsplit, p.nsets), MAX_SPLIT));
+    if (const char* ov = getenv("PSAM_TC_NSPLIT")) {      // experiment knob: column splits per row tile
+        const int v = atoi(ov);
+        if (v >= 1) nsplit = min(min(v, p.nsets), MAX_SPLIT);
+    }
     TcParams t{a_img, b_img, scale, p.counts, p.eff_modes, p.scores, p.assign, p.status,
                p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit, p.qry, p.slice_stride, p.row_stride, p.C};
     const int grid = min(sms, L.ntiles * nsplit);
