@@ -40,7 +40,7 @@ N_ROTATE = 4            # distinct input volumes cycled through the timed region
 
 def workload_desc(cfg, n_gpus):
     return {
-        "workload": (f"{cfg['name']}: 1 support + {cfg['Q']} query slices per GPU, ViT-B/14 features "
+        "workload": (f"{cfg['name']}: 1 support + {cfg['Q']} query slices per GPU, /14 patch features "
                      f"{cfg['h']}x{cfg['w']}x{cfg['C']}, {cfg['L']} labels (bg 'gridconv' + fg 'gridconv+'/'mask' "
                      f"decided on device), ws={cfg['ws']}, upsample {cfg['img_size']}->1024, prompts for every "
                      f"component (use_cca=False, point_mode=both)"),
