@@ -176,7 +176,7 @@ __device__ __forceinline__ void run_stats(const uint32_t* __restrict__ bits, con
     }
 }
 
-__global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
+__global__ void __maxnreg__(48) k_components(CompParams P)
 {
     __shared__ int s_rowstart[MAX_OUT + 1];
     extern __shared__ uint32_t s_dyn[];          // 2 * KEY_WORDS words (64 KB, opt-in)

@@ -106,3 +106,33 @@ def test_shard_range_partitions():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_part_assign_matches_reference_rule():
+    """dataloaders/common.py:241-249: int((z - z_min) // ((z_max - z_min) / npart)), clamped, 0 on a degenerate extent"""
+    for z_min, z_max, npart in ((10, 40, 3), (0, 7, 3), (5, 5, 3), (3, 50, 4), (12, 13, 3)):
+        for z in range(z_min - 3, z_max + 4):
+            try:
+                ref = int((z - z_min) // ((z_max - z_min) / npart))
+            except ZeroDivisionError:
+                ref = 0
+            ref = 0 if ref < 0 else (npart - 1 if ref >= npart else ref)
+            assert engine.part_assign(z, z_min, z_max, npart) == ref
+
+
+def test_packed_layouts_round_trip_on_cpu():
+    """the one-buffer layouts the collectives move: views alias the packed storage, split inverts alloc"""
+    tab = ops.proto_table_alloc(4, 7, 16, "cpu")
+    tab["protos"].fill_(1.5); tab["counts"].copy_(torch.arange(4, dtype=torch.int32)); tab["status"].zero_(); tab["eff_modes"].fill_(2)
+    clone = tab["packed"].clone()
+    t2 = ops.proto_table_alloc(4, 7, 16, "cpu")
+    t2["packed"].copy_(clone)
+    assert torch.equal(t2["protos"], tab["protos"]) and torch.equal(t2["counts"], tab["counts"])
+    assert torch.equal(t2["eff_modes"], tab["eff_modes"]) and tab["protos"].shape == (4, 7, 16)
+    buf, hdr, recs = ops.records_alloc(5, 3, "cpu")
+    hdr[2, 0] = 7
+    recs[4, 2, 95] = 9
+    h2, r2 = ops.split_records(buf.clone(), 3)
+    assert h2.shape == (5, 64) and r2.shape == (5, 3, 96) and h2[2, 0] == 7 and r2[4, 2, 95] == 9
+    p = engine.PendingGather.done((hdr, recs))
+    assert p.result()[0] is hdr
