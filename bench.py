@@ -202,8 +202,7 @@ def gpu_arm(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings off stdout: one JSON line only
         if args.nccl_channels > 0:
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))   # MB-sized messages: few CTAs suffice
         dist.init_process_group("nccl", device_id=dev)
