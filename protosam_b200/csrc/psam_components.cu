@@ -176,7 +176,51 @@ __device__ __forceinline__ void run_stats(const uint32_t* __restrict__ bits, con
     }
 }
 
-__global__ void __maxnreg__(48) k_components(CompParams P)
+// The same statistics computed by ONE thread (used where every thread of the CTA owns a different run: thousands
+// of independent loads in flight instead of one run per warp).  Words are taken four at a time so that the
+// mask-word and per-word-statistics loads of a group are issued before any of them is consumed.
+__device__ __forceinline__ void run_stats_thread(const uint32_t* __restrict__ bits, const float* __restrict__ pfg,
+                                                 const uint2* __restrict__ wstat, int out, int wpr, int y, int s, int e,
+                                                 unsigned long long& sum, unsigned long long& best)
+{
+    sum = 0; best = 0;
+    const int wa = s >> 5, wb = e >> 5;
+    const uint32_t* brow = bits + (size_t)y * wpr;
+    const uint2* srow = wstat ? wstat + (size_t)y * wpr : nullptr;
+    for (int j0 = wa; j0 <= wb; j0 += 4) {
+        uint32_t m[4];
+        uint2 st[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = min(j0 + u, wb);
+            m[u] = brow[j];
+            st[u] = srow ? srow[j] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
+            if (j > wb) break;
+            const int lo = (j == wa) ? (s & 31) : 0, hi = (j == wb) ? (e & 31) : 31;
+            const uint32_t fm = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+            if (srow && (m[u] & ~fm) == 0u) {
+                sum += st[u].x;
+                const uint32_t k = st[u].y >> 5, x = j * 32 + 31 - (st[u].y & 31);
+                const uint32_t pb = (k == 16777216u) ? 0x3f800000u : (0x3f000000u + ((k - 8388608u)));
+                best = max(best, ((unsigned long long)pb << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * out + x)));
+            } else {
+                for (int b = lo; b <= hi; ++b) {
+                    const int x = j * 32 + b;
+                    const float pv = pfg[(size_t)y * out + x];
+                    sum += (unsigned long long)(pv * 16777216.0f);
+                    best = max(best, ((unsigned long long)__float_as_uint(pv) << 32) |
+                                         (unsigned long long)(0xFFFFFFFFu - (unsigned)(y * out + x)));
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
 {
     __shared__ int s_rowstart[MAX_OUT + 1];
     extern __shared__ uint32_t s_dyn[];          // 2 * KEY_WORDS words (64 KB, opt-in)
@@ -318,8 +362,18 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
         }
 
         // ---- S3: materialise the runs -----------------------------------------------------
-        for (int y = wid; y < out; y += CT / 32) {
-            const uint32_t word = lane < wpr ? bits[(size_t)y * wpr + lane] : 0u;
+        for (int yb = wid; yb < out; yb += 4 * (CT / 32)) {
+          uint32_t wq[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {     // four independent row loads in flight per warp
+              const int y = yb + u * (CT / 32);
+              wq[u] = (lane < wpr && y < out) ? bits[(size_t)y * wpr + lane] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int y = yb + u * (CT / 32);
+            if (y >= out) break;
+            const uint32_t word = wq[u];
             uint32_t prev_msb = __shfl_up_sync(0xffffffffu, word >> 31, 1);
             if (lane == 0) prev_msb = 0;
             uint32_t next_lsb = __shfl_down_sync(0xffffffffu, word & 1u, 1);
@@ -344,6 +398,7 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
                 run_e[ei] = (uint16_t)(lane * 32 + b);
                 ++ei;
             }
+          }
         }
         for (int i = tid; i < key_words; i += CT) s_bitmap[i] = 0u;
         __syncthreads();
@@ -482,25 +537,23 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
             acc[r] = a;
         }
         __syncthreads();
-        for (int i = wid; i < total; i += CT / 32) {
+        for (int i = tid; i < total; i += CT) {          // one thread per run
             const int root = parent[i];
             const int slot = P.use_cca ? (root == sel_root ? 0 : -1) : (rank[root] < P.max_cc ? rank[root] : -1);
             if (slot < 0) continue;
             const int y = run_y[i], s = run_s[i], e = run_e[i];
             unsigned long long acc_p, best;
-            run_stats(bits, pfg, wst, out, wpr, y, s, e, lane, acc_p, best);
-            if (lane == 0) {
-                Acc* a = acc + slot;
-                const unsigned int len = e - s + 1;
-                atomicAdd(&a->area, len);
-                atomicAdd(&a->sumx, (unsigned long long)(s + e) * len / 2);
-                atomicAdd(&a->sumy, (unsigned long long)y * len);
-                atomicAdd(&a->sump, acc_p);
-                atomicMax(&a->best, best);
-                atomicMin(&a->minx, (unsigned)s); atomicMax(&a->maxx, (unsigned)e);
-                atomicMin(&a->miny, (unsigned)y); atomicMax(&a->maxy, (unsigned)y);
-                if (i == root) a->root = root;
-            }
+            run_stats_thread(bits, pfg, wst, out, wpr, y, s, e, acc_p, best);
+            Acc* a = acc + slot;
+            const unsigned int len = e - s + 1;
+            atomicAdd(&a->area, len);
+            atomicAdd(&a->sumx, (unsigned long long)(s + e) * len / 2);
+            atomicAdd(&a->sumy, (unsigned long long)y * len);
+            atomicAdd(&a->sump, acc_p);
+            atomicMax(&a->best, best);
+            atomicMin(&a->minx, (unsigned)s); atomicMax(&a->maxx, (unsigned)e);
+            atomicMin(&a->miny, (unsigned)y); atomicMax(&a->maxy, (unsigned)y);
+            if (i == root) a->root = root;
         }
         __syncthreads();
 
