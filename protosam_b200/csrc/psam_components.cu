@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
             uint32_t prev_msb = __shfl_up_sync(0xffffffffu, word >> 31, 1);
             if (lane == 0) prev_msb = 0;
             const uint32_t starts = word & ~((word << 1) | prev_msb);
-            const int tot = warp_sum_i(__popc(starts));
+            const int tot = __reduce_add_sync(0xffffffffu, __popc(starts));
             npix += __popc(word);
             if (lane < wpr) {
                 const uint32_t inv = ~word;
@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
             if (lane == 31) next_lsb = 0;
             uint32_t starts = word & ~((word << 1) | prev_msb);
             uint32_t ends = word & ~((word >> 1) | (next_lsb << 31));
+            // ends before this lane = starts before this lane - (a run is open on entry to this lane)
             int si = s_rowstart[y] + warp_excl_scan_i(__popc(starts), lane);
-            int ei = s_rowstart[y] + warp_excl_scan_i(__popc(ends), lane);
+            int ei = si - (int)(prev_msb & word & 1u);
             while (starts) {
                 const int b = __ffs(starts) - 1;
                 starts &= starts - 1;
