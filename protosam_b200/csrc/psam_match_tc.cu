@@ -47,11 +47,24 @@ namespace psam {
 
 namespace tc {
 
+// k-block depth: 64 bf16 = 128-byte rows (SWIZZLE_128B, 2 stages of 96 KB) or 32 bf16 = 64-byte rows (SWIZZLE_64B,
+// 4 stages of 48 KB: the same bytes in flight, but a stage is requested three MMA batches ahead instead of one)
+#ifndef PSAM_TC_BK
+#define PSAM_TC_BK 32
+#endif
 constexpr int BM = 128;                          // query rows per tile = TMEM lanes
-constexpr int BK = 64;                           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int BK = PSAM_TC_BK;                   // bf16 elements per k-block = one swizzle row
+static_assert(BK == 32 || BK == 64, "k-block depth");
 constexpr int NCH = 256;                         // prototype columns per TMEM accumulator buffer
-constexpr int STAGES = 2;
-constexpr int GROUP_BYTES = 2048;                // 8 rows x 128 B: hi plane (1024 B) then lo plane (1024 B)
+constexpr int STAGES = BK == 64 ? 2 : 4;
+constexpr int ROW_BYTES = BK * 2;                // one operand row of a k-block
+constexpr int CHUNKS = ROW_BYTES / 16;           // 16-byte chunks per row
+constexpr int PLANE_BYTES = 8 * ROW_BYTES;       // 8 rows of one plane = one swizzle atom
+constexpr int GROUP_BYTES = 2 * PLANE_BYTES;     // 8 rows: hi plane then lo plane
+constexpr uint64_t UMMA_LAYOUT = BK == 64 ? 2 : 4;   // cute::UMMA::LayoutType SWIZZLE_128B / SWIZZLE_64B
+
+// physical 16-byte chunk of logical chunk c in row r of an 8-row atom (Swizzle<3,4,3> / Swizzle<2,4,3>)
+__host__ __device__ __forceinline__ int swz(int r, int c) { return BK == 64 ? (c ^ r) : (c ^ ((r >> 1) & 3)); }
 constexpr int A_STAGE_BYTES = BM / 8 * GROUP_BYTES;    // 32 KB
 constexpr int B_STAGE_BYTES = NCH / 8 * GROUP_BYTES;   // 64 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -144,12 +157,12 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major operand, 128-byte swizzle, 8-row groups GROUP_BYTES apart (cute::UMMA::SmemDescriptor:
+// K-major operand, 128- or 64-byte swizzle, 8-row groups GROUP_BYTES apart (cute::UMMA::SmemDescriptor:
 // start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(GROUP_BYTES >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+           ((uint64_t)1 << 46) | (UMMA_LAYOUT << 61);
 }
 
 // cute::UMMA::InstrDescriptor: D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
@@ -189,7 +202,7 @@ __device__ __forceinline__ float pack_row(const float* __restrict__ src, bool va
                                           uint8_t* __restrict__ group0, size_t kb_stride, int r)
 {
     float ssq = 0.f;
-    for (int ch = lane; ch < KB * 8; ch += 32) {
+    for (int ch = lane; ch < KB * CHUNKS; ch += 32) {
         const int k0 = ch * 8;
         float v[8];
         if (valid && k0 < C) {
@@ -204,10 +217,10 @@ __device__ __forceinline__ float pack_row(const float* __restrict__ src, bool va
         for (int i = 0; i < 8; ++i) ssq = fmaf(v[i], v[i], ssq);
         uint4 hi, lo;
         split8(v, hi, lo);
-        const int kb = ch >> 3, c = ch & 7;
-        uint8_t* dst = group0 + (size_t)kb * kb_stride + r * 128 + ((c ^ r) << 4);
+        const int kb = ch / CHUNKS, c = ch % CHUNKS;
+        uint8_t* dst = group0 + (size_t)kb * kb_stride + r * ROW_BYTES + (swz(r, c) << 4);
         *reinterpret_cast<uint4*>(dst) = hi;
-        *reinterpret_cast<uint4*>(dst + 1024) = lo;
+        *reinterpret_cast<uint4*>(dst + PLANE_BYTES) = lo;
     }
     return warp_sum(ssq);
 }
@@ -392,8 +405,8 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
                         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t a_hi = make_sdesc(a_addr + k * 32), a_lo = make_sdesc(a_addr + 1024 + k * 32);
-                            const uint64_t b_hi = make_sdesc(b_addr + k * 32), b_lo = make_sdesc(b_addr + 1024 + k * 32);
+                            const uint64_t a_hi = make_sdesc(a_addr + k * 32), a_lo = make_sdesc(a_addr + PLANE_BYTES + k * 32);
+                            const uint64_t b_hi = make_sdesc(b_addr + k * 32), b_lo = make_sdesc(b_addr + PLANE_BYTES + k * 32);
                             tc_mma(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);
                             tc_mma(d_tmem, a_lo, b_hi, idesc, 1);
                             tc_mma(d_tmem, a_hi, b_lo, idesc, 1);
@@ -510,6 +523,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        if (h >= CHUNKS / 4) continue;             // 64-byte rows: one chunk per row and thread
                         const int k0 = kb * BK + (cq + 4 * h) * 8;
                         const bool in = ok[j] && k0 < p.C;
                         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -529,7 +543,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
+                        for (int h = 0; h < CHUNKS / 4; ++h) {
                             const float4 x = cur[j * 4 + h * 2], y = cur[j * 4 + h * 2 + 1];
                             const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
                             if (first) {
@@ -538,9 +552,9 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
                             }
                             uint4 hi, lo;
                             split8(v, hi, lo);
-                            uint8_t* dst = sa + (j * 8 + cw) * GROUP_BYTES + r * 128 + (((cq + 4 * h) ^ r) << 4);
+                            uint8_t* dst = sa + (j * 8 + cw) * GROUP_BYTES + r * ROW_BYTES + (swz(r, cq + 4 * h) << 4);
                             *reinterpret_cast<uint4*>(dst) = hi;
-                            *reinterpret_cast<uint4*>(dst + 1024) = lo;
+                            *reinterpret_cast<uint4*>(dst + PLANE_BYTES) = lo;
                         }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
                     __syncwarp();
