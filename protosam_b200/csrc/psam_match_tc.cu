@@ -21,12 +21,12 @@
 //
 // Structure (one persistent CTA per SM):
 //   k_pack_protos  prototype rows of all sets, concatenated (each set padded to 16 columns) so one B matrix serves
-//                  every set -> bf16 hi/lo planes already in the 128-byte-swizzled K-major layout the MMA reads.
+//                  every set -> bf16 hi/lo planes already in the swizzled K-major layout the MMA reads.
 //   k_pack_query   [algo 2] the same for the query rows, per (128-row tile, 64-channel block), plus the per-row
 //                  scale 20/max(|q|,1e-4).
 //   k_match_tc     warp 0: one thread streams operand blocks global -> shared with cp.async.bulk
-//                  (TMA engine, mbarrier complete_tx) through a 2-stage ring;
-//                  warp 1: one thread issues tcgen05.mma (M=128, N<=256, K=16, 12 per k-block)
+//                  (TMA engine, mbarrier complete_tx) through a 4-stage ring of 48 KB stages;
+//                  warp 1: one thread issues tcgen05.mma (M=128, N<=256, K=16, 6 per 32-channel k-block)
 //                  into one of two 256-column TMEM accumulators and commits to mbarriers;
 //                  warps 2-5: epilogue -- tcgen05.ld 16 columns at a time, scale, exp2, running
 //                  sum(e), sum(e*d), max/argmax per set, store one float per (row, set).
