@@ -7,8 +7,9 @@
 One step = one synthetic volume of the CHAOS-MRI-shaped config (BASELINE.json configs[1]): kernel 1
 over the support slice for 4 labels (8 prototype sets), kernel 2 over 32 query slices, kernel 3 over
 the 128 resulting coarse maps -> prompt records.  With N ranks every rank takes 32 further slices of
-the same volume (weak scaling): rank 0 computes the prototypes and broadcasts them (NCCL), every rank
-matches its slices, prompt records are gathered to rank 0.
+the same volume (weak scaling): one rank computes the prototypes and broadcasts them (NCCL), every rank
+matches its slices, prompt records are gathered to rank 0.  `--lanes` volumes are in flight per GPU on
+separate CUDA streams, each replayed from CUDA graphs (engine.GraphedVolumeStep).
 
 `value` is timed with inputs resident in HBM; `e2e` goes through the same engine from pinned host
 buffers with the host->device copies and the device->host read of the records inside the timed
@@ -23,7 +24,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
