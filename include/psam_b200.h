@@ -95,6 +95,21 @@ int psam_alp_prototypes(const float* sup_x, const int64_t* sup_x_strides, const 
                         uint8_t* survive, float* pooled,
                         void* workspace, size_t workspace_bytes, psam_stream_t stream);
 
+/* The same with a shot selector per set (host [nsets]: -1 = every shot, k = shot k only).  FewShotSeg.forward
+ * matches the foreground once per shot (models/grid_proto_fewshot.py:244-262): a set restricted to shot k takes its
+ * local windows, its AUTO_FG decision and its single global row from that shot alone, exactly like calling the
+ * module with supp_fts[:, k] and that shot's mask. */
+int psam_alp_prototypes_shots(const float* sup_x, const int64_t* sup_x_strides, const float* sup_y,
+                              int nsets, const int32_t* set_modes, const int32_t* set_shots, int S, int C, int h, int w,
+                              int kh, int kw, int auto_kh, int auto_kw, float thresh,
+                              float* protos, int32_t* counts, int32_t* eff_modes, int32_t* status,
+                              uint8_t* survive, float* pooled,
+                              void* workspace, size_t workspace_bytes, psam_stream_t stream);
+
+/* Element-wise max over the per-shot foreground scores (grid_proto_fewshot.py:263-270).  scores [Q, L*(1+S), HW] with
+ * the sets of label l ordered (bg_l, fg_l shot 0, ..., fg_l shot S-1) -> logits [Q*L, 2, HW] = (bg_l, max_s fg_l,s). */
+int psam_combine_shots(const float* scores, int Q, int L, int S, int HW, float* logits, psam_stream_t stream);
+
 /* Nearest-neighbour resize of the support masks to feature resolution, as FewShotSeg.forward does before calling
  * the ALP module (F.interpolate(mask, fts_size, mode='nearest'), models/grid_proto_fewshot.py:228-231):
  * src [n,H,W] -> dst [n,h,w], source index = min(floor(dst * (float)in / out), in - 1). */

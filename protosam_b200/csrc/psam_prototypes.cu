@@ -18,6 +18,7 @@ namespace psam {
 constexpr int kMaxSets = 128;
 struct SetModes {
     int8_t m[kMaxSets];
+    int8_t shot[kMaxSets];   // -1: the set uses every shot; k: only shot k (FewShotSeg's per-shot foreground calls)
 };
 
 // ------------------------------------------------------------------------------------
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256) k_pool_mask(const float* __restrict__ sup
     __shared__ float s_wsum[8];
 
     int mode = modes.m[set];
+    const int sel = modes.shot[set];
     if (mode == PSAM_MODE_AUTO_FG) {
         // F.avg_pool2d(mask, kernel_size).max() >= thresh   (grid_proto_fewshot.py:254-256)
         const int agh = h / akh, agw = w / akw, AN = S * agh * agw;
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(256) k_pool_mask(const float* __restrict__ sup
         int hit = 0;
         for (int n = tid; n < AN; n += 256) {
             int s = n / (agh * agw), r = n % (agh * agw), gy = r / agw, gx = r % agw;
+            if (sel >= 0 && s != sel) continue;
             const float* p = y + ((size_t)s * h + gy * akh) * w + gx * akw;
             float acc = 0.0f;
             for (int dy = 0; dy < akh; ++dy)
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(256) k_pool_mask(const float* __restrict__ sup
                 for (int dx = 0; dx < kw; ++dx) acc = __fadd_rn(acc, p[dy * w + dx]);
             float f = __fdiv_rn(acc, div);
             pooled[(size_t)set * N + n] = f;
-            flag = locals && (f > thresh);
+            flag = locals && (f > thresh) && (sel < 0 || s == sel);
             survive[(size_t)set * N + n] = (uint8_t)(f > thresh);
         }
         int ex = warp_excl_scan_i(flag, lane);
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(256) k_pool_mask(const float* __restrict__ sup
     }
     if (tid == 0) {
         plocal[set] = running;
-        counts[set] = running + (globals ? S : 0);
+        counts[set] = running + (globals ? (sel < 0 ? S : 1) : 0);
         eff_modes[set] = mode;
         status[set] = (mode == PSAM_MODE_GRIDCONV && running == 0) ? PSAM_SET_EMPTY : 0;
     }
@@ -177,11 +180,12 @@ __global__ void __launch_bounds__(256) k_pool_feat(const float* __restrict__ sup
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_global_partial(const float* __restrict__ sup_x, int64_t xs_s, int64_t xs_c,
                                                         int64_t xs_y, int64_t xs_x, const float* __restrict__ sup_y,
-                                                        const int32_t* __restrict__ eff_modes, int S, int C, int h,
-                                                        int w, float* __restrict__ partial)
+                                                        const int32_t* __restrict__ eff_modes, SetModes modes, int S,
+                                                        int C, int h, int w, float* __restrict__ partial)
 {
     const int yy = blockIdx.x, s = blockIdx.y, set = blockIdx.z, tid = threadIdx.x;
     if (eff_modes[set] == PSAM_MODE_GRIDCONV) return;
+    if (modes.shot[set] >= 0 && s != modes.shot[set]) return;
     const float* m = sup_y + (((size_t)set * S + s) * h + yy) * w;
     const float* base = sup_x + s * xs_s + (int64_t)yy * xs_y;
     float* dst = partial + (((size_t)set * S + s) * h + yy) * C;
@@ -198,11 +202,13 @@ __global__ void __launch_bounds__(256) k_global_partial(const float* __restrict_
 __global__ void __launch_bounds__(256) k_global_final(const float* __restrict__ partial,
                                                       const float* __restrict__ ysum,
                                                       const int32_t* __restrict__ eff_modes,
-                                                      const int32_t* __restrict__ plocal, int S, int C, int h,
-                                                      int cap_rows, float* __restrict__ protos)
+                                                      const int32_t* __restrict__ plocal, SetModes modes, int S, int C,
+                                                      int h, int cap_rows, float* __restrict__ protos)
 {
     const int s = blockIdx.x, set = blockIdx.y, tid = threadIdx.x;
     if (eff_modes[set] == PSAM_MODE_GRIDCONV) return;
+    const int sel = modes.shot[set];
+    if (sel >= 0 && s != sel) return;
     __shared__ float s_red[8];
     const float* src = partial + ((size_t)set * S + s) * h * C;
     const float den = ysum[set * S + s] + 1e-5f;
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(256) k_global_final(const float* __restrict__ 
     // safe_norm for the grid modes (:158); cosine_similarity's clamp_min(eps=1e-4) for 'mask'
     // (:59) -- the same arithmetic.
     float nrm = fmaxf(sqrtf(ss), 1e-4f);
-    float* dst = protos + ((size_t)set * cap_rows + plocal[set] + s) * C;
+    float* dst = protos + ((size_t)set * cap_rows + plocal[set] + (sel >= 0 ? 0 : s)) * C;
 #pragma unroll
     for (int j = 0; j < kMaxCPerThread; ++j) {
         int c = tid + j * 256;
@@ -319,9 +325,47 @@ __global__ void __launch_bounds__(256) k_mask_nearest(const float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------
+// FewShotSeg.forward with several shots (models/grid_proto_fewshot.py:244-270): the background set uses all shots,
+// the foreground is matched once per shot and the scores are combined with an element-wise max.  Sets of label l
+// are (bg_l, fg_l shot 0, ..., fg_l shot S-1); the result is the [Q*L, 2, HW] logits tensor of the caller.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_combine_shots(const float* __restrict__ scores, int Q, int L, int S, int HW,
+                                                       float* __restrict__ logits)
+{
+    const size_t total = (size_t)Q * L * HW;
+    const int nsets = L * (1 + S);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int p = (int)(i % HW), l = (int)((i / HW) % L);
+        const size_t q = i / ((size_t)HW * L);
+        const float* src = scores + (q * nsets + (size_t)l * (1 + S)) * HW + p;
+        float m = src[(size_t)HW];
+        for (int s = 1; s < S; ++s) {
+            const float v = src[(size_t)(1 + s) * HW];
+            m = (v > m || v != v) ? v : m;          // torch.max propagates NaN
+        }
+        float* dst = logits + ((q * L + l) * 2) * HW + p;
+        dst[0] = src[0];
+        dst[HW] = m;
+    }
+}
+
 }  // namespace psam
 
 using namespace psam;
+
+extern "C" int psam_combine_shots(const float* scores, int Q, int L, int S, int HW, float* logits, psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(scores && logits, "psam_combine_shots: null pointer");
+    PSAM_CHECK_ARG(Q >= 1 && L >= 1 && S >= 1 && HW >= 1, "psam_combine_shots: bad shape");
+    const size_t total = (size_t)Q * L * HW;
+    const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
+    PSAM_PROF_BEGIN(stream);
+    k_combine_shots<<<grid, 256, 0, stream>>>(scores, Q, L, S, HW, logits);
+    PSAM_CHECK_LAUNCH("k_combine_shots");
+    return PSAM_OK;
+}
 
 extern "C" int psam_mask_nearest(const float* src, int n, int H, int W, int h, int w, float* dst, psam_stream_t stream_)
 {
@@ -348,11 +392,38 @@ extern "C" size_t psam_alp_prototypes_workspace(int nsets, int S, int C, int h, 
     return b + 256;
 }
 
+static int alp_prototypes_impl(const float* sup_x, const int64_t* xs, const float* sup_y, int nsets,
+                               const int32_t* set_modes, const int32_t* set_shots, int S, int C, int h, int w, int kh,
+                               int kw, int auto_kh, int auto_kw, float thresh, float* protos, int32_t* counts,
+                               int32_t* eff_modes, int32_t* status, uint8_t* survive, float* pooled,
+                               void* workspace, size_t workspace_bytes, psam_stream_t stream_);
+
 extern "C" int psam_alp_prototypes(const float* sup_x, const int64_t* xs, const float* sup_y, int nsets,
                                    const int32_t* set_modes, int S, int C, int h, int w, int kh, int kw,
                                    int auto_kh, int auto_kw, float thresh, float* protos, int32_t* counts,
                                    int32_t* eff_modes, int32_t* status, uint8_t* survive, float* pooled,
-                                   void* workspace, size_t workspace_bytes, psam_stream_t stream_)
+                                   void* workspace, size_t workspace_bytes, psam_stream_t stream)
+{
+    return alp_prototypes_impl(sup_x, xs, sup_y, nsets, set_modes, nullptr, S, C, h, w, kh, kw, auto_kh, auto_kw, thresh,
+                               protos, counts, eff_modes, status, survive, pooled, workspace, workspace_bytes, stream);
+}
+
+extern "C" int psam_alp_prototypes_shots(const float* sup_x, const int64_t* xs, const float* sup_y, int nsets,
+                                         const int32_t* set_modes, const int32_t* set_shots, int S, int C, int h, int w,
+                                         int kh, int kw, int auto_kh, int auto_kw, float thresh, float* protos,
+                                         int32_t* counts, int32_t* eff_modes, int32_t* status, uint8_t* survive,
+                                         float* pooled, void* workspace, size_t workspace_bytes, psam_stream_t stream)
+{
+    PSAM_CHECK_ARG(set_shots, "psam_alp_prototypes_shots: null set_shots");
+    return alp_prototypes_impl(sup_x, xs, sup_y, nsets, set_modes, set_shots, S, C, h, w, kh, kw, auto_kh, auto_kw, thresh,
+                               protos, counts, eff_modes, status, survive, pooled, workspace, workspace_bytes, stream);
+}
+
+static int alp_prototypes_impl(const float* sup_x, const int64_t* xs, const float* sup_y, int nsets,
+                               const int32_t* set_modes, const int32_t* set_shots, int S, int C, int h, int w, int kh,
+                               int kw, int auto_kh, int auto_kw, float thresh, float* protos, int32_t* counts,
+                               int32_t* eff_modes, int32_t* status, uint8_t* survive, float* pooled,
+                               void* workspace, size_t workspace_bytes, psam_stream_t stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(sup_x && xs && sup_y && set_modes && protos && counts && eff_modes && status && survive && pooled,
@@ -366,6 +437,9 @@ extern "C" int psam_alp_prototypes(const float* sup_x, const int64_t* xs, const 
     for (int i = 0; i < nsets; ++i) {
         PSAM_CHECK_ARG(set_modes[i] >= 0 && set_modes[i] <= 3, "psam_alp_prototypes: invalid mode %d", set_modes[i]);
         modes.m[i] = (int8_t)set_modes[i];
+        const int shot = set_shots ? set_shots[i] : -1;
+        PSAM_CHECK_ARG(shot >= -1 && shot < S && shot < 127, "psam_alp_prototypes: set %d selects shot %d of %d", i, shot, S);
+        modes.shot[i] = (int8_t)shot;
         any_auto |= set_modes[i] == PSAM_MODE_AUTO_FG;
     }
     if (any_auto)
@@ -396,11 +470,11 @@ extern "C" int psam_alp_prototypes(const float* sup_x, const int64_t* xs, const 
         PSAM_CHECK_LAUNCH("k_pool_feat");
     }
     PSAM_PROF_BEGIN(stream);
-    k_global_partial<<<dim3(h, S, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], sup_y, eff_modes, S, C,
-                                                            h, w, partial);
+    k_global_partial<<<dim3(h, S, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], sup_y, eff_modes, modes,
+                                                            S, C, h, w, partial);
     PSAM_CHECK_LAUNCH("k_global_partial");
     PSAM_PROF_BEGIN(stream);
-    k_global_final<<<dim3(S, nsets), 256, 0, stream>>>(partial, ysum, eff_modes, plocal, S, C, h, cap_rows, protos);
+    k_global_final<<<dim3(S, nsets), 256, 0, stream>>>(partial, ysum, eff_modes, plocal, modes, S, C, h, cap_rows, protos);
     PSAM_CHECK_LAUNCH("k_global_final");
     return PSAM_OK;
 }

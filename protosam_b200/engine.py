@@ -121,7 +121,7 @@ class CoarseVolumeEngine:
         self.max_cc, self.max_runs = int(max_cc), int(max_runs)
         self.fg_mode, self.match_algo, self.group = fg_mode, match_algo, group
         self.protos: Optional[dict] = None
-        self.n_labels = 0
+        self.n_labels, self.n_shots = 0, 1
         self._ws = None
 
     # -- distributed helpers -------------------------------------------------------------------
@@ -132,28 +132,33 @@ class CoarseVolumeEngine:
 
     # -- support side ----------------------------------------------------------------------------
     def set_support(self, sup_feats: torch.Tensor, fg_masks: torch.Tensor, src: int = 0, broadcast: bool = True):
-        """sup_feats [S,h,w,C] channels-last support features (S = 1, the reference's n_shots);
+        """sup_feats [S,h,w,C] channels-last support features (S shots; the reference configs use 1);
         fg_masks [L,S,h,w] foreground masks at feature resolution (nearest-downsampled like
         grid_proto_fewshot.py:228-231).  Computes on `src`, broadcasts to the other ranks."""
         S, h, w, C = sup_feats.shape
         assert (h, w) == (self.h, self.w)
-        if S != 1:
-            raise NotImplementedError("the engine follows the reference configs (n_shots=1); use the "
-                                      "MultiProtoAsConv drop-in for multi-shot support sets")
         L = fg_masks.shape[0]
-        self.n_labels = L
+        self.n_labels, self.n_shots = L, S
         world, rank = self._world()
         sup_x = sup_feats.permute(0, 3, 1, 2)                      # logical [S,C,h,w], channels-last storage
         fg = fg_masks.reshape(L, 1, S, h, w).to(torch.float32)
-        sup_y = torch.cat([1.0 - fg, fg], dim=1).reshape(2 * L, S, h, w)   # (bg_0, fg_0, bg_1, fg_1, ...)
-        modes = ["gridconv", self.fg_mode] * L
+        if S == 1:
+            sup_y = torch.cat([1.0 - fg, fg], dim=1).reshape(2 * L, S, h, w)   # (bg_0, fg_0, bg_1, fg_1, ...)
+            modes, shots = ["gridconv", self.fg_mode] * L, None
+        else:
+            # several shots (grid_proto_fewshot.py:239-264): background from all shots at once, foreground once per
+            # shot (that shot's features and mask only), element-wise max over the shots afterwards
+            sup_y = torch.cat([1.0 - fg] + [fg] * S, dim=1).reshape(L * (1 + S), S, h, w)
+            modes = (["gridconv"] + [self.fg_mode] * S) * L
+            shots = ([-1] + list(range(S))) * L
+        nsets = sup_y.shape[0]
         if world == 1 or rank == src:
             protos = ops.alp_prototypes(sup_x, sup_y, modes, (self.val_wsize, self.val_wsize), FG_THRESH,
-                                        auto_ksize=self.kernel_size)
+                                        auto_ksize=self.kernel_size, shots=shots)
         else:
             gh, gw = h // self.val_wsize, w // self.val_wsize
             N = S * gh * gw
-            protos = ops.proto_table_alloc(2 * L, N + S, C, sup_feats.device)
+            protos = ops.proto_table_alloc(nsets, N + S, C, sup_feats.device)
             protos.update(N=N, gh=gh, gw=gw, S=S, C=C)
         self.protos = protos
         if broadcast:
@@ -173,6 +178,8 @@ class CoarseVolumeEngine:
         Q, h, w, C = qry_feats.shape
         scores, _, _ = ops.alp_match(qry_feats.view(Q, h * w, C), self.protos, want_assign=False,
                                      algo=self.match_algo)
+        if getattr(self, "n_shots", 1) > 1:
+            return ops.combine_shots(scores, self.n_labels, self.n_shots).view(Q * self.n_labels, 2, h, w)
         return scores.view(Q * self.n_labels, 2, h, w)
 
     def prompts_from_logits(self, logits: torch.Tensor, n_alloc=None, return_packed=False):

@@ -65,10 +65,11 @@ def proto_table_alloc(nsets, cap_rows, C, device):
                 counts=ints(0), eff_modes=ints(1), status=ints(2), cap_rows=cap_rows)
 
 
-def alp_prototypes(sup_x, sup_y, modes, ksize, thresh, auto_ksize=None):
+def alp_prototypes(sup_x, sup_y, modes, ksize, thresh, auto_ksize=None, shots=None):
     """sup_x [S,C,h,w] (any strides; channels-last is the fast case), sup_y [nsets,S,h,w],
-    modes: list of 'mask' | 'gridconv' | 'gridconv+' | 'auto_fg'.  Returns a dict of device
-    tensors (see include/psam_b200.h, psam_alp_prototypes)."""
+    modes: list of 'mask' | 'gridconv' | 'gridconv+' | 'auto_fg'; shots: optional list, per set -1 (every shot)
+    or the one shot the set is restricted to.  Returns a dict of device tensors (see include/psam_b200.h,
+    psam_alp_prototypes / psam_alp_prototypes_shots)."""
     L = _lib.load()
     _need_cuda(sup_x, sup_y)
     S, C, h, w = sup_x.shape
@@ -90,12 +91,31 @@ def alp_prototypes(sup_x, sup_y, modes, ksize, thresh, auto_ksize=None):
     ws = _ws(L.psam_alp_prototypes_workspace(nsets, S, C, h, w, kh, kw), dev)
     strides = (ctypes.c_int64 * 4)(*sup_x.stride())
     mode_arr = (ctypes.c_int32 * nsets)(*[MODE_IDS[m] if isinstance(m, str) else int(m) for m in modes])
-    rc = L.psam_alp_prototypes(_ptr(sup_x), strides, _ptr(sup_y), nsets, mode_arr, S, C, h, w, kh, kw, akh, akw,
-                               float(thresh), _ptr(out["protos"]), _ptr(out["counts"]), _ptr(out["eff_modes"]),
-                               _ptr(out["status"]), _ptr(out["survive"]), _ptr(out["pooled"]), _ptr(ws),
-                               ws.numel(), _stream())
+    tail = (S, C, h, w, kh, kw, akh, akw, float(thresh), _ptr(out["protos"]), _ptr(out["counts"]),
+            _ptr(out["eff_modes"]), _ptr(out["status"]), _ptr(out["survive"]), _ptr(out["pooled"]), _ptr(ws), ws.numel(),
+            _stream())
+    if shots is None:
+        rc = L.psam_alp_prototypes(_ptr(sup_x), strides, _ptr(sup_y), nsets, mode_arr, *tail)
+    else:
+        assert len(shots) == nsets
+        shot_arr = (ctypes.c_int32 * nsets)(*[int(v) for v in shots])
+        rc = L.psam_alp_prototypes_shots(_ptr(sup_x), strides, _ptr(sup_y), nsets, mode_arr, shot_arr, *tail)
     _lib.check(rc, "psam_alp_prototypes")
     out["_ws"] = ws          # keep alive until the stream has consumed it
+    return out
+
+
+def combine_shots(scores, L, S):
+    """scores [Q, L*(1+S), HW] with sets (bg_l, fg_l shot 0..S-1) -> logits [Q*L, 2, HW] = (bg_l, max over shots of
+    fg_l), the element-wise max of grid_proto_fewshot.py:263-270."""
+    lib = _lib.load()
+    _need_cuda(scores)
+    scores = scores.contiguous()
+    Q, nsets, HW = scores.shape
+    assert nsets == L * (1 + S)
+    out = torch.empty((Q * L, 2, HW), dtype=torch.float32, device=scores.device)
+    rc = lib.psam_combine_shots(_ptr(scores), Q, L, S, HW, _ptr(out), _stream())
+    _lib.check(rc, "psam_combine_shots")
     return out
 
 

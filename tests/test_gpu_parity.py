@@ -643,3 +643,43 @@ def test_graphed_volume_step_replays_equal_eager_run():
     e2.set_support(_t(vol.sup), _t(vol.fg))
     ha, ra = e2.run_sharded(_t(vol.qry), 3, async_op=True).result()
     assert torch.equal(ha, h1) and torch.equal(ra, r1)
+
+
+@pytest.mark.parametrize("fg_mode", ["auto_fg", "mask"])
+def test_engine_multi_shot_matches_reference_rule(fg_mode):
+    """n_shots > 1 (grid_proto_fewshot.py:239-270): background prototypes from all shots at once, foreground once per
+    shot (that shot alone: its windows, its mode decision, its single global row), element-wise max over the shots"""
+    h = w = 16
+    C, img, L, S, Q = 64, 128, 2, 3, 2
+    sup = synth.layer_norm(synth.gaussian_like(41, (S, h, w, C)))
+    qry = (np.roll(sup[:Q], 1, 1) + 0.3 * synth.gaussian_like(42, (Q, h, w, C))).astype(np.float32)
+    fg = np.zeros((L, S, h, w), np.float32)
+    fg[0, 0, 2:8, 2:8] = 1; fg[0, 1, 6:12, 5:11] = 1; fg[0, 2, 9, 9] = 1      # shot 2 of label 0: single pixel -> 'mask'
+    fg[1, 0, 10:14, 1:5] = 1; fg[1, 2, 3:9, 8:14] = 1                          # shot 1 of label 1: empty mask
+    eng = CoarseVolumeEngine((h, w), img, out_size=256, val_wsize=2, proto_grid_size=8, fg_mode=fg_mode)
+    pr = eng.set_support(_t(sup), _t(fg))
+    assert pr["protos"].shape[0] == L * (1 + S)
+    logits = eng.match(_t(qry)).cpu().numpy().reshape(Q, L, 2, h, w)
+    eff = [_lib.MODE_NAMES[int(e)] for e in pr["eff_modes"].cpu().numpy()]
+    ks = [h // 8, w // 8]
+    for l in range(L):
+        bg_mask = (1.0 - fg[l])[None, :, None]                                    # [1,S,1,h,w], all shots
+        sx_all = np.transpose(sup, (0, 3, 1, 2))[None, :, None]
+        for q in range(Q):
+            qq = np.transpose(qry[q], (2, 0, 1))[None]
+            ref_bg, _, _, _ = O.alp_forward(qq, sx_all, bg_mask, "gridconv", 0.95, ks, isval=True, val_wsize=2)
+            np.testing.assert_allclose(logits[q, l, 0], ref_bg[0, 0], atol=MAP_TOL, rtol=0)
+            per_shot = []
+            for s in range(S):
+                if fg_mode == "mask":
+                    mode = "mask"
+                else:   # the caller's rule on that shot's mask (grid_proto_fewshot.py:250-256)
+                    pooled = O.get_prototypes(np.transpose(sup[s:s + 1], (0, 3, 1, 2)), fg[l, s][None, None], "gridconv+", ks, 0.95)["pooled"]
+                    mode = "gridconv+" if (pooled >= 0.95).any() else "mask"
+                assert eff[l * (1 + S) + 1 + s] == mode
+                sx = np.transpose(sup[s:s + 1], (0, 3, 1, 2))[None, :, None]
+                r, _, _, _ = O.alp_forward(qq, sx, fg[l, s][None, None, None], mode, 0.95, ks, isval=True, val_wsize=2)
+                per_shot.append(r[0, 0])
+            np.testing.assert_allclose(logits[q, l, 1], np.max(np.stack(per_shot), 0), atol=MAP_TOL, rtol=0)
+    got = eng.decode(*eng.run(_t(qry)))
+    assert len(got) == Q and len(got[0]) == L
