@@ -215,6 +215,16 @@ int psam_components(const uint32_t* maskbits, const float* p_fg, const uint64_t*
                     psam_image_hdr* hdr, psam_prompt_rec* recs, int32_t* labels_out,
                     void* workspace, size_t workspace_bytes, psam_stream_t stream);
 
+/* Records -> the prompt tensors of SamPredictor.predict_torch (models/segment_anything/predictor.py:136-167), in
+ * SAM's input frame: ResizeLongestSide.apply_coords / apply_boxes (models/segment_anything/utils/transforms.py:40-62,
+ * 140-148) scale x by new_w/old_w and y by new_h/old_h in double precision, torch.as_tensor(dtype=float) rounds to
+ * fp32.  point_mode 0 = 'conf', 1 = 'centroid', 2 = 'both' (npts = 1, 1, 2; models/ProtoSAM.py:349-450).
+ *   points [n_img,max_cc,npts,2] float, labels [n_img,max_cc,npts] int32 (1 = foreground), boxes [n_img,max_cc,4]
+ *   float XYXY; slots beyond the image's n_rec are zero. */
+int psam_records_to_sam(const psam_image_hdr* hdr, const psam_prompt_rec* recs, int n_img, int max_cc,
+                        int point_mode, int old_h, int old_w, int target_length,
+                        float* points, int32_t* labels, float* boxes, psam_stream_t stream);
+
 /* Both stages for a batch of images: what the volume engine calls.  p_fg / maskbits live in
  * the workspace. */
 size_t psam_coarse_to_prompts_workspace(int n_img, int out, int max_runs, int max_cc);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "psam_upsample_softmax": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_sz, c_p]),
     "psam_prompts_workspace": (c_sz, [c_i] * 4),
     "psam_components": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "psam_records_to_sam": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "psam_coarse_to_prompts_workspace": (c_sz, [c_i] * 4),
     "psam_coarse_to_prompts": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
 }

@@ -609,6 +609,47 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Records -> the tensors SamPredictor.predict_torch takes (models/segment_anything/predictor.py:136-167):
+// ResizeLongestSide.apply_coords / apply_boxes (models/segment_anything/utils/transforms.py:40-62) scale x by
+// new_w/old_w and y by new_h/old_h in double precision, torch.as_tensor(..., dtype=torch.float) rounds to fp32.
+// One thread per (image, component slot); slots beyond n_rec are zero-filled.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_records_to_sam(const psam_image_hdr* __restrict__ hdr,
+                                                        const psam_prompt_rec* __restrict__ recs, int n_img, int max_cc,
+                                                        int point_mode, double sx, double sy, float* __restrict__ points,
+                                                        int32_t* __restrict__ labels, float* __restrict__ boxes)
+{
+    const int npts = point_mode == 2 ? 2 : 1;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_img * max_cc) return;
+    const int img = i / max_cc, r = i - img * max_cc;
+    float* pt = points + (size_t)i * npts * 2;
+    int32_t* lb = labels + (size_t)i * npts;
+    float* bx = boxes + (size_t)i * 4;
+    if (r >= hdr[img].n_rec) {
+        for (int k = 0; k < npts * 2; ++k) pt[k] = 0.f;
+        for (int k = 0; k < npts; ++k) lb[k] = 0;
+        for (int k = 0; k < 4; ++k) bx[k] = 0.f;
+        return;
+    }
+    const psam_prompt_rec rec = recs[i];
+    int k = 0;
+    if (point_mode != 1) {          // most confident point
+        pt[k++] = (float)((double)rec.conf_pt[0] * sx);
+        pt[k++] = (float)((double)rec.conf_pt[1] * sy);
+    }
+    if (point_mode != 0) {          // centroid
+        pt[k++] = (float)(rec.centroid[0] * sx);
+        pt[k++] = (float)(rec.centroid[1] * sy);
+    }
+    for (int j = 0; j < npts; ++j) lb[j] = 1;
+    bx[0] = (float)((double)rec.box[0] * sx);
+    bx[1] = (float)((double)rec.box[1] * sy);
+    bx[2] = (float)((double)rec.box[2] * sx);
+    bx[3] = (float)((double)rec.box[3] * sy);
+}
+
 }  // namespace psam
 
 using namespace psam;
@@ -720,4 +761,23 @@ extern "C" int psam_coarse_to_prompts(const float* logits, int n_img, int h, int
     if (rc) return rc;
     return psam_components(bits, p_fg, wstat, n_img, out, use_cca, max_cc, max_runs, hdr, recs, nullptr, rest,
                            workspace_bytes - cv.used(), stream);
+}
+
+extern "C" int psam_records_to_sam(const psam_image_hdr* hdr, const psam_prompt_rec* recs, int n_img, int max_cc,
+                                   int point_mode, int old_h, int old_w, int target_length, float* points,
+                                   int32_t* labels, float* boxes, psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(hdr && recs && points && labels && boxes, "psam_records_to_sam: null pointer");
+    PSAM_CHECK_ARG(n_img >= 1 && max_cc >= 1 && point_mode >= 0 && point_mode <= 2 && old_h >= 1 && old_w >= 1 &&
+                       target_length >= 1, "psam_records_to_sam: bad argument");
+    // ResizeLongestSide.get_preprocess_shape (models/segment_anything/utils/transforms.py:140-148)
+    const double scale = (double)target_length * 1.0 / (double)(old_h > old_w ? old_h : old_w);
+    const int new_h = (int)((double)old_h * scale + 0.5), new_w = (int)((double)old_w * scale + 0.5);
+    const double sx = (double)new_w / (double)old_w, sy = (double)new_h / (double)old_h;
+    PSAM_PROF_BEGIN(stream);
+    k_records_to_sam<<<(n_img * max_cc + 255) / 256, 256, 0, stream>>>(hdr, recs, n_img, max_cc, point_mode, sx, sy, points,
+                                                                       labels, boxes);
+    PSAM_CHECK_LAUNCH("k_records_to_sam");
+    return PSAM_OK;
 }

@@ -244,6 +244,27 @@ def coarse_to_prompts(logits, mid, out=1024, use_cca=False, max_cc=DEFAULT_MAX_C
     return hdr[:n], recs[:n]
 
 
+POINT_MODE_IDS = {"conf": 0, "centroid": 1, "both": 2}
+
+
+def records_to_sam(hdr, recs, point_mode="both", original_size=(1024, 1024), target_length=1024):
+    """Device records -> (points [n,max_cc,npts,2] f32, labels [n,max_cc,npts] i32, boxes [n,max_cc,4] f32) in SAM's
+    input frame, ready for SamPredictor.predict_torch (one call per image with batch = its n_rec components).  No host
+    round trip: the prompts never leave the device."""
+    L = _lib.load()
+    hdr, recs = hdr.contiguous(), recs.contiguous()
+    n, max_cc = recs.shape[0], recs.shape[1]
+    npts = 2 if point_mode == "both" else 1
+    dev = recs.device
+    points = torch.empty((n, max_cc, npts, 2), dtype=torch.float32, device=dev)
+    labels = torch.empty((n, max_cc, npts), dtype=torch.int32, device=dev)
+    boxes = torch.empty((n, max_cc, 4), dtype=torch.float32, device=dev)
+    rc = L.psam_records_to_sam(_ptr(hdr), _ptr(recs), n, max_cc, POINT_MODE_IDS[point_mode], int(original_size[0]),
+                               int(original_size[1]), int(target_length), _ptr(points), _ptr(labels), _ptr(boxes), _stream())
+    _lib.check(rc, "psam_records_to_sam")
+    return points, labels, boxes
+
+
 def decode_headers(hdr_u8) -> np.ndarray:
     """device/host uint8 [n,64] -> numpy structured array (host sync on .cpu())."""
     return np.frombuffer(hdr_u8.detach().cpu().numpy().tobytes(), dtype=HDR_DTYPE)

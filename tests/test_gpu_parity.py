@@ -683,3 +683,34 @@ def test_engine_multi_shot_matches_reference_rule(fg_mode):
             np.testing.assert_allclose(logits[q, l, 1], np.max(np.stack(per_shot), 0), atol=MAP_TOL, rtol=0)
     got = eng.decode(*eng.run(_t(qry)))
     assert len(got) == Q and len(got[0]) == L
+
+
+@pytest.mark.parametrize("point_mode", ["conf", "centroid", "both"])
+@pytest.mark.parametrize("orig", [(1024, 1024), (672, 512)])
+def test_records_to_sam_tensors_match_reference_transforms(point_mode, orig):
+    """device prompt tensors == ResizeLongestSide.apply_coords / apply_boxes (segment_anything/utils/transforms.py:40-62)
+    followed by torch.as_tensor(dtype=float) (predictor.py:143-150), applied to the reference-format prompts"""
+    low = (synth.gaussian_like(77, (3, 2, 24, 24)) * 6).astype(np.float32)
+    low[2] = -5.0 * np.abs(low[2]) * np.array([-1.0, 1.0], np.float32)[:, None, None]     # image 2: no foreground
+    hdr, recs = ops.coarse_to_prompts(_t(low), 96, 256, use_cca=False, max_cc=64)
+    pts, labs, boxes = ops.records_to_sam(hdr, recs, point_mode, original_size=orig, target_length=1024)
+    H, R = ops.decode_headers(hdr), ops.decode_records(recs)
+    old_h, old_w = orig
+    scale = 1024 * 1.0 / max(old_h, old_w)
+    new_h, new_w = int(old_h * scale + 0.5), int(old_w * scale + 0.5)
+    pts, labs, boxes = pts.cpu().numpy(), labs.cpu().numpy(), boxes.cpu().numpy()
+    assert int(H["n_rec"][2]) == 0 and not pts[2].any() and not boxes[2].any()
+    for i in range(3):
+        sp = PR.prompts_from_records(H[i], R[i], False, point_mode)
+        n = int(H["n_rec"][i])
+        if n == 0:
+            continue
+        coords = sp.points.astype(float).copy()
+        coords[..., 0] = coords[..., 0] * (new_w / old_w)
+        coords[..., 1] = coords[..., 1] * (new_h / old_h)
+        assert np.array_equal(pts[i, :n], coords.astype(np.float32))
+        b = sp.boxes.reshape(-1, 2, 2).astype(float)
+        b[..., 0] = b[..., 0] * (new_w / old_w)
+        b[..., 1] = b[..., 1] * (new_h / old_h)
+        assert np.array_equal(boxes[i, :n], b.reshape(-1, 4).astype(np.float32))
+        assert (labs[i, :n] == 1).all() and not labs[i, n:].any()
