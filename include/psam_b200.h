@@ -110,6 +110,12 @@ int psam_alp_prototypes_shots(const float* sup_x, const int64_t* sup_x_strides, 
  * the sets of label l ordered (bg_l, fg_l shot 0, ..., fg_l shot S-1) -> logits [Q*L, 2, HW] = (bg_l, max_s fg_l,s). */
 int psam_combine_shots(const float* scores, int Q, int L, int S, int HW, float* logits, psam_stream_t stream);
 
+/* DINOv2 token hand-off of FewShotSeg.get_features (models/grid_proto_fewshot.py:90-98): tokens [B, h*w, C]
+ * (= the channels-last feature map) -> out [B, oh, ow, C], bilinear, align_corners=False; the reference does this when
+ * the map has fewer than 32x32 tokens (BASELINE config 1: 18x18 -> 32x32).  Upsampling only. */
+int psam_tokens_to_features(const float* tokens, int B, int h, int w, int C, int oh, int ow, float* out,
+                            psam_stream_t stream);
+
 /* Nearest-neighbour resize of the support masks to feature resolution, as FewShotSeg.forward does before calling
  * the ALP module (F.interpolate(mask, fts_size, mode='nearest'), models/grid_proto_fewshot.py:228-231):
  * src [n,H,W] -> dst [n,h,w], source index = min(floor(dst * (float)in / out), in - 1). */

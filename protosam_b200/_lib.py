@@ -40,6 +40,7 @@ SIGNATURES = {
     "psam_alp_prototypes_shots": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f,
                                         c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "psam_combine_shots": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "psam_tokens_to_features": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "psam_mask_nearest": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "psam_alp_proto_grid": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
     "psam_alp_match_workspace": (c_sz, [c_i] * 6),

@@ -350,9 +350,62 @@ __global__ void __launch_bounds__(256) k_combine_shots(const float* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------
+// DINOv2 token hand-off (models/grid_proto_fewshot.py:90-98): x_norm_patchtokens [B, h*w, C] is already the
+// channels-last feature map; when it has fewer than 32x32 tokens the reference resizes it bilinearly
+// (align_corners=False) to 32x32.  Same arithmetic as ATen's CPU kernel (source index = scale*(dst+0.5)-0.5 clamped at
+// 0, horizontal lerps then the vertical one, each fma(a, w0, b*w1)); threads run along C, so every load and store is
+// coalesced.  grid = (ow, oh, B).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void bil_src(int in, int out, int o, int& i0, int& i1, float& w0, float& w1)
+{
+    if (in == out) { i0 = i1 = o; w0 = 1.f; w1 = 0.f; return; }
+    const float scale = __fdiv_rn((float)in, (float)out);
+    float r = __fmaf_rn(scale, __fadd_rn((float)o, 0.5f), -0.5f);
+    if (r < 0.f) r = 0.f;
+    i0 = min((int)floorf(r), in - 1);
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    w1 = fminf(fmaxf(__fsub_rn(r, (float)i0), 0.f), 1.f);
+    w0 = __fsub_rn(1.f, w1);
+}
+
+__global__ void __launch_bounds__(256) k_tokens_bilinear(const float* __restrict__ tok, int h, int w, int C, int oh, int ow,
+                                                         float* __restrict__ out)
+{
+    const int ox = blockIdx.x, oy = blockIdx.y, b = blockIdx.z;
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    bil_src(h, oh, oy, y0, y1, wy0, wy1);
+    bil_src(w, ow, ox, x0, x1, wx0, wx1);
+    const float* base = tok + (size_t)b * h * w * C;
+    const float* p00 = base + ((size_t)y0 * w + x0) * C;
+    const float* p01 = base + ((size_t)y0 * w + x1) * C;
+    const float* p10 = base + ((size_t)y1 * w + x0) * C;
+    const float* p11 = base + ((size_t)y1 * w + x1) * C;
+    float* dst = out + (((size_t)b * oh + oy) * ow + ox) * C;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float r0 = __fmaf_rn(p00[c], wx0, __fmul_rn(p01[c], wx1));
+        const float r1 = __fmaf_rn(p10[c], wx0, __fmul_rn(p11[c], wx1));
+        dst[c] = __fmaf_rn(r0, wy0, __fmul_rn(r1, wy1));
+    }
+}
+
 }  // namespace psam
 
 using namespace psam;
+
+extern "C" int psam_tokens_to_features(const float* tokens, int B, int h, int w, int C, int oh, int ow, float* out,
+                                       psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(tokens && out, "psam_tokens_to_features: null pointer");
+    PSAM_CHECK_ARG(B >= 1 && B <= 65535 && h >= 1 && w >= 1 && C >= 1 && oh >= h && ow >= w && oh <= 65535,
+                   "psam_tokens_to_features: bad shape (upsampling only)");
+    PSAM_PROF_BEGIN(stream);
+    k_tokens_bilinear<<<dim3(ow, oh, B), 256, 0, stream>>>(tokens, h, w, C, oh, ow, out);
+    PSAM_CHECK_LAUNCH("k_tokens_bilinear");
+    return PSAM_OK;
+}
 
 extern "C" int psam_combine_shots(const float* scores, int Q, int L, int S, int HW, float* logits, psam_stream_t stream_)
 {

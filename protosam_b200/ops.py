@@ -119,6 +119,25 @@ def combine_shots(scores, L, S):
     return out
 
 
+DEFAULT_FEATURE_SIZE = 32          # util/consts.py:1
+
+
+def tokens_to_features(tokens, feature_size=DEFAULT_FEATURE_SIZE):
+    """FewShotSeg.get_features' hand-off (grid_proto_fewshot.py:90-98): x_norm_patchtokens [B, HW, C] -> channels-last
+    features [B, h, w, C]; maps with fewer than feature_size^2 tokens are resized bilinearly to feature_size^2."""
+    L = _lib.load()
+    _need_cuda(tokens)
+    B, HW, C = tokens.shape
+    h = w = int(HW ** 0.5)
+    tokens = tokens.contiguous()
+    if HW >= feature_size ** 2:
+        return tokens.view(B, h, w, C)
+    out = torch.empty((B, feature_size, feature_size, C), dtype=torch.float32, device=tokens.device)
+    rc = L.psam_tokens_to_features(_ptr(tokens), B, h, w, C, feature_size, feature_size, _ptr(out), _stream())
+    _lib.check(rc, "psam_tokens_to_features")
+    return out
+
+
 def mask_nearest(masks, h, w):
     """F.interpolate(masks, (h, w), mode='nearest') for float masks [..., H, W] (grid_proto_fewshot.py:228-231)."""
     L = _lib.load()

@@ -714,3 +714,13 @@ def test_records_to_sam_tensors_match_reference_transforms(point_mode, orig):
         b[..., 1] = b[..., 1] * (new_h / old_h)
         assert np.array_equal(boxes[i, :n], b.reshape(-1, 4).astype(np.float32))
         assert (labs[i, :n] == 1).all() and not labs[i, n:].any()
+
+
+def test_tokens_to_features_matches_aten_bilinear():
+    """the DINOv2 token hand-off of BASELINE config 1 (18x18 tokens -> 32x32 features, grid_proto_fewshot.py:96-98)"""
+    tok = synth.gaussian_like(3, (2, 18 * 18, 48))
+    got = ops.tokens_to_features(_t(tok)).cpu().numpy()                        # [2,32,32,48] channels-last
+    ref = O.upsample_bilinear(np.transpose(tok.reshape(2, 18, 18, 48), (0, 3, 1, 2)), 32)   # ATen-CPU restatement
+    assert got.shape == (2, 32, 32, 48) and np.array_equal(np.transpose(got, (0, 3, 1, 2)), ref)
+    big = _t(synth.gaussian_like(4, (1, 37 * 37, 16)))
+    assert ops.tokens_to_features(big).data_ptr() == big.data_ptr()              # >= 32x32 tokens: a view, no copy
