@@ -468,8 +468,9 @@ def gpu_arm(args, cfg):
     model = {   # kernel -> (bound, algorithmic work per launch, note)
         "k_match_tc": ("tensor", flops_match, "2*HW*C*sum(P) per slice; executed = 3x (split-bf16 passes)"),
         "k_match_simt": ("tensor", flops_match, "2*HW*C*sum(P) per slice on CUDA cores"),
-        "k_exact_blocks": ("hbm", n_img * (8.0 * h * w + out * out / 8.0) + 4.0 * n_fg,
-                           "per image: 8*h*w logits + out^2/8 mask bits + 4*n_fg probabilities"),
+        "k_blocks_warp": ("hbm", n_img * (8.0 * h * w + out * out / 8.0) + 4.0 * n_fg,
+                          "per image: 8*h*w logits + out^2/8 mask bits + 4*n_fg probabilities (upper bound: p_fg is "
+                          "written only where kernel 3b reads it); the kernel is CUDA-core issue-bound, see profiles/"),
         "k_components": ("hbm", n_img * (out * out / 8.0 + 64.0) + 4.0 * n_fg + 96.0 * n_cc,
                          "per image: out^2/8 mask bits + 4*n_fg probabilities + 96 B per component"),
         "k_pack_query": ("hbm", 8.0 * Q * h * w * C, "4*C*HW read + 4*C*HW operand image written per slice"),

@@ -220,7 +220,7 @@ __device__ __forceinline__ void run_stats_thread(const uint32_t* __restrict__ bi
     }
 }
 
-__global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
+__global__ void __maxnreg__(48) k_components(CompParams P)
 {
     __shared__ int s_rowstart[MAX_OUT + 1];
     extern __shared__ uint32_t s_dyn[];          // 2 * KEY_WORDS words (64 KB, opt-in)
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
     __shared__ int s_misc[16];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int out = P.out, wpr = out >> 5, bw = (out + 1) >> 1;
+    const int out = P.out, wpr = (out + 31) >> 5, bw = (out + 1) >> 1;
     const int key_words = (bw * bw + 31) >> 5;
     const size_t so = (size_t)blockIdx.x * P.max_runs;
     uint16_t* run_s = P.run_s + so;
@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(CT, 1) k_components(CompParams P)
             const int tot = __reduce_add_sync(0xffffffffu, __popc(starts));
             npix += __popc(word);
             if (lane < wpr) {
-                const uint32_t inv = ~word;
+                // bits beyond the last column (out % 32 != 0) are neither foreground nor background
+                const uint32_t inv = ~word & ((lane == wpr - 1 && (out & 31)) ? (0xffffffffu >> (32 - (out & 31))) : 0xffffffffu);
                 if (inv) {
                     bany = 1;
                     const unsigned int x0 = lane * 32 + (__ffs(inv) - 1), x1 = lane * 32 + 31 - __clz(inv);
@@ -688,7 +689,7 @@ extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, cons
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(maskbits && p_fg && hdr && recs && workspace, "psam_components: null pointer");
     PSAM_CHECK_ARG(n_img >= 1, "psam_components: n_img %d", n_img);
-    PSAM_CHECK_ARG(out >= 32 && out <= MAX_OUT && out % 32 == 0, "psam_components: out=%d must be a multiple of 32 in [32,%d]", out, MAX_OUT);
+    PSAM_CHECK_ARG(out >= 1 && out <= MAX_OUT, "psam_components: out=%d must be in [1,%d]", out, MAX_OUT);
     PSAM_CHECK_ARG(max_cc >= 1 && max_cc <= (1 << 18), "psam_components: max_cc %d", max_cc);
     PSAM_CHECK_ARG(max_runs >= 1 && max_runs <= (1 << 24), "psam_components: max_runs %d", max_runs);
     const int ctas = comp_grid(n_img);
@@ -734,8 +735,8 @@ extern "C" size_t psam_coarse_to_prompts_workspace(int n_img, int out, int max_r
     if (n_img <= 0 || out <= 0) return 0;
     size_t b = 0;
     b += align_up(sizeof(float) * (size_t)n_img * out * out, 256);            // p_fg
-    b += align_up(sizeof(uint32_t) * (size_t)n_img * out * (out / 32), 256);  // mask bits
-    b += align_up(sizeof(uint2) * (size_t)n_img * out * (out / 32), 256);     // per-word statistics
+    b += align_up(sizeof(uint32_t) * (size_t)n_img * out * ((out + 31) / 32), 256);  // mask bits
+    b += align_up(sizeof(uint2) * (size_t)n_img * out * ((out + 31) / 32), 256);     // per-word statistics
     b += align_up(psam_upsample_workspace(n_img, out), 256);                  // block work list
     b += psam_prompts_workspace(n_img, out, max_runs, max_cc);
     return b + 256;
@@ -752,8 +753,8 @@ extern "C" int psam_coarse_to_prompts(const float* logits, int n_img, int h, int
     }
     Carver cv(workspace);
     float* p_fg = cv.take<float>((size_t)n_img * out * out);
-    uint32_t* bits = cv.take<uint32_t>((size_t)n_img * out * (out / 32));
-    uint64_t* wstat = cv.take<uint64_t>((size_t)n_img * out * (out / 32));
+    uint32_t* bits = cv.take<uint32_t>((size_t)n_img * out * ((out + 31) / 32));
+    uint64_t* wstat = cv.take<uint64_t>((size_t)n_img * out * ((out + 31) / 32));
     const size_t upw = psam_upsample_workspace(n_img, out);
     char* upws = cv.take<char>(upw);
     char* rest = static_cast<char*>(workspace) + cv.used();

@@ -56,7 +56,7 @@ constexpr int BM = 128;                          // query rows per tile = TMEM l
 constexpr int BK = PSAM_TC_BK;                   // bf16 elements per k-block = one swizzle row
 static_assert(BK == 32 || BK == 64, "k-block depth");
 constexpr int NCH = 256;                         // prototype columns per TMEM accumulator buffer
-constexpr int STAGES = BK == 64 ? 2 : 4;
+constexpr int MAX_STAGES = BK == 64 ? 2 : 4;
 constexpr int ROW_BYTES = BK * 2;                // one operand row of a k-block
 constexpr int CHUNKS = ROW_BYTES / 16;           // 16-byte chunks per row
 constexpr int PLANE_BYTES = 8 * ROW_BYTES;       // 8 rows of one plane = one swizzle atom
@@ -68,7 +68,7 @@ __host__ __device__ __forceinline__ int swz(int r, int c) { return BK == 64 ? (c
 constexpr int A_STAGE_BYTES = BM / 8 * GROUP_BYTES;    // 32 KB
 constexpr int B_STAGE_BYTES = NCH / 8 * GROUP_BYTES;   // 64 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for the 1024-byte alignment
+__host__ __device__ constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024; }  // + slack for the 1024-byte alignment
 constexpr int MAX_SETS = 128;
 constexpr int MAX_SPLIT = 8;
 constexpr int THREADS = 192;
@@ -305,7 +305,10 @@ __device__ __forceinline__ void fold16(const float (&v)[16], int nvalid, int nba
 //                 split them into bf16 hi/lo, store them swizzled into the A stage (generic proxy ->
 //                 fence.proxy.async -> mbarrier), and accumulate the row norms on the way: the query is read from
 //                 HBM exactly once by the whole path and no operand image of it is ever written.
-template <bool kFused>
+// STAGES operand stages of 48 KB: 4 fill the SM's shared memory (fastest GEMM when it runs alone); 3 leave ~80 KB, which
+// is what the ALU-bound prompt kernels of ANOTHER volume (k_blocks_warp, k_components) need to be resident on the same SM
+// while the tensor pipe works -- the step is then max(tensor, ALU) instead of their sum.
+template <bool kFused, int STAGES>
 __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_tc(const TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -634,7 +637,7 @@ size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fu
     return align_up(L.a_bytes, 1024) + align_up(L.b_bytes, 1024) + align_up(L.scale_bytes, 1024) + 1024;
 }
 
-template <bool kFused>
+template <bool kFused, int kStages>
 static int launch_gemm(const tc::TcParams& t, int grid, cudaStream_t stream)
 {
     using namespace tc;
@@ -642,17 +645,34 @@ static int launch_gemm(const tc::TcParams& t, int grid, cudaStream_t stream)
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {       // once per device
-        cudaError_t e = cudaFuncSetAttribute(k_match_tc<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_match_tc<kFused, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem_bytes(kStages));
         if (e != cudaSuccess) {
-            set_error("k_match_tc: cudaFuncSetAttribute(%d bytes): %s", SMEM_BYTES, cudaGetErrorString(e));
+            set_error("k_match_tc: cudaFuncSetAttribute(%d bytes): %s", smem_bytes(kStages), cudaGetErrorString(e));
             return PSAM_ERR_LAUNCH;
         }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     PSAM_PROF_BEGIN(stream);
-    k_match_tc<kFused><<<grid, kFused ? THREADS_FUSED : THREADS, SMEM_BYTES, stream>>>(t);
+    k_match_tc<kFused, kStages><<<grid, kFused ? THREADS_FUSED : THREADS, smem_bytes(kStages), stream>>>(t);
     PSAM_CHECK_LAUNCH(kFused ? "k_match_tc_fused" : "k_match_tc");
     return PSAM_OK;
+}
+
+// operand stages of the packed-image GEMM: 3 by default (co-residency, see k_match_tc); PSAM_TC_STAGES=4 is the
+// experiment knob for the stand-alone optimum
+static int gemm_stages()
+{
+    using tc::MAX_STAGES;
+    static int v = 0;
+    if (v == 0) {
+        v = MAX_STAGES >= 4 ? 3 : MAX_STAGES;
+        if (const char* ov = getenv("PSAM_TC_STAGES")) {
+            const int x = atoi(ov);
+            if (x == 3 || x == 4) v = x <= MAX_STAGES ? x : MAX_STAGES;
+        }
+    }
+    return v;
 }
 
 int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, bool fused, cudaStream_t stream)
@@ -693,7 +713,9 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     TcParams t{a_img, b_img, scale, p.counts, p.eff_modes, p.scores, p.assign, p.status,
                p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit, p.qry, p.slice_stride, p.row_stride, p.C};
     const int grid = min(sms, L.ntiles * nsplit);
-    return fused ? launch_gemm<true>(t, grid, stream) : launch_gemm<false>(t, grid, stream);
+    if (fused) return launch_gemm<true, MAX_STAGES>(t, grid, stream);
+    if (MAX_STAGES >= 4 && gemm_stages() == 3) return launch_gemm<false, (MAX_STAGES >= 4 ? 3 : MAX_STAGES)>(t, grid, stream);
+    return launch_gemm<false, MAX_STAGES>(t, grid, stream);
 }
 
 }  // namespace psam

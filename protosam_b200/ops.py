@@ -196,9 +196,10 @@ def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False, f
     assert two == 2
     dev = logits.device
     p_fg = torch.empty((n, out, out), dtype=torch.float32, device=dev) if want_p_fg else None
-    bits = torch.empty((n, out, out // 32), dtype=torch.int32, device=dev)
+    wpr = (out + 31) // 32
+    bits = torch.empty((n, out, wpr), dtype=torch.int32, device=dev)
     probs2 = torch.empty((n, 2, out, out), dtype=torch.float32, device=dev) if want_probs2 else None
-    wstat = torch.zeros((n, out, out // 32), dtype=torch.int64, device=dev) if want_wstat else None
+    wstat = torch.zeros((n, out, wpr), dtype=torch.int64, device=dev) if want_wstat else None
     if fg_only and p_fg is not None:
         p_fg.zero_()
     ws = _ws(L.psam_upsample_workspace(n, int(out)), dev)

@@ -344,7 +344,17 @@ def test_engine_variant_of_upsample_equals_full_variant(h, S):
     p_fg, bits, _, wstat = ops.upsample_softmax(_t(low), S, 1024, fg_only=True, want_wstat=True)
     assert torch.equal(bits, bits_full)
     mask = torch.from_numpy(np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little").reshape(3, 1024, 1024)).bool().to(DEV)
-    assert torch.equal(p_fg[mask], p_full[mask])
+    # the engine variant writes p_fg only where kernel 3b can read it per pixel: always in words that are not full,
+    # in full words only next to a non-full word above/below (or at a block's first/last row); what it writes is exact
+    partial = (bits != -1).repeat_interleave(32, dim=2) & mask
+    assert partial.any() and torch.equal(p_fg[partial], p_full[partial])
+    written = mask & (p_fg != 0)
+    assert torch.equal(p_fg[written], p_full[written])
+    full_w = (bits == -1)
+    lonely = full_w.clone()
+    lonely[:, 1:-1] &= ~(full_w[:, :-2] & full_w[:, 2:])          # full words without two full vertical neighbours
+    lonely_px = lonely.repeat_interleave(32, dim=2)
+    assert torch.equal(p_fg[lonely_px], p_full[lonely_px])
     for use_cca in (False, True):
         a = ops.components(bits, p_fg, use_cca=use_cca, max_cc=4096, wstat=wstat)
         b = ops.components(bits_full, p_full, use_cca=use_cca, max_cc=4096)
