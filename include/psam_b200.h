@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PSAM_ABI_VERSION 1
+#define PSAM_ABI_VERSION 2
 
 typedef void* psam_stream_t; /* cudaStream_t */
 
@@ -206,8 +206,15 @@ typedef struct psam_image_hdr {
  * win (probs2 must be NULL).  The mask, p_fg at foreground pixels and wstat are identical to fg_only=0. */
 size_t psam_upsample_workspace(int n_img, int out);
 
+/* prob_mode: which probability p_fg / wstat (and through them the component confidences and the most confident
+ * points) carry.  The mask is argmax of the 2-way softmax in both modes. */
+#define PSAM_PROB_SOFTMAX        0 /* ProtoSAM: softmax(logits)[1]                        models/ProtoSAM.py:599        */
+#define PSAM_PROB_SOFTMAX_TWICE  1 /* ProtoMedSAM: need_softmax turns the logits into probabilities first and
+                                      cca / get_connected_components apply softmax(1) to them AGAIN
+                                      (models/ProtoMedSAM.py:178-187, util/utils.py:62-63, 486): softmax(softmax(logits))[1] */
+
 int psam_upsample_softmax(const float* logits, int n_img, int h, int w, int mid, int out,
-                          float* p_fg, uint32_t* maskbits, float* probs2, uint64_t* wstat, int fg_only,
+                          float* p_fg, uint32_t* maskbits, float* probs2, uint64_t* wstat, int fg_only, int prob_mode,
                           void* workspace, size_t workspace_bytes, psam_stream_t stream);
 
 /* max_runs: capacity of the per-CTA run table (foreground row segments per image). */
@@ -231,14 +238,75 @@ int psam_records_to_sam(const psam_image_hdr* hdr, const psam_prompt_rec* recs, 
                         int point_mode, int old_h, int old_w, int target_length,
                         float* points, int32_t* labels, float* boxes, psam_stream_t stream);
 
+/* Compact form of a batch's headers + records: what leaves the GPU (device->host copy, gather to rank 0).  The dense
+ * [n_img, max_cc] record array is almost all empty slots; `packed` holds
+ *   n_alloc headers (image i's hdr.reserved = index of its first record; images >= n_img zeroed)
+ *   one psam_packed_tail
+ *   `capacity` records, the live ones of all images in image order.
+ * psam_packed_bytes gives the size.  More than `capacity` live records set PSAM_PACKED_OVERFLOW (the surplus is
+ * dropped; the dense arrays are untouched, so the caller can fall back to them). */
+typedef struct psam_packed_tail {
+    int32_t total;       /* live records of the batch                    */
+    int32_t capacity;
+    int32_t flags;       /* PSAM_PACKED_* */
+    int32_t n_img;
+    int32_t reserved[12];
+} psam_packed_tail;     /* 64 bytes */
+
+#define PSAM_PACKED_OVERFLOW 1
+
+size_t psam_packed_bytes(int n_alloc, int capacity);
+
+int psam_compact_records(const psam_image_hdr* hdr, const psam_prompt_rec* recs, int n_img, int n_alloc, int max_cc,
+                         int capacity, void* packed, psam_stream_t stream);
+
 /* Both stages for a batch of images: what the volume engine calls.  p_fg / maskbits live in
  * the workspace. */
 size_t psam_coarse_to_prompts_workspace(int n_img, int out, int max_runs, int max_cc);
 
 int psam_coarse_to_prompts(const float* logits, int n_img, int h, int w, int mid, int out,
-                           int use_cca, int max_cc, int max_runs,
+                           int use_cca, int prob_mode, int max_cc, int max_runs,
                            psam_image_hdr* hdr, psam_prompt_rec* recs,
                            void* workspace, size_t workspace_bytes, psam_stream_t stream);
+
+/* --------------------------------------------------------------------------------------
+ * Optional prompt variants of ProtoSAM.forward (off in the reference's configs, config_ssl_upload.py:93,102).  They
+ * consume what psam_upsample_softmax (fg_only = 0, probs2) and psam_components (labels_out) leave on the device.
+ * ------------------------------------------------------------------------------------ */
+
+/* One negative-point candidate.  32 bytes. */
+typedef struct psam_neg_point {
+    int64_t pt[2];      /* x, y; -1 when there is none                                              */
+    float   p;          /* the (possibly thresholded) background probability torch.topk picked      */
+    int32_t has;        /* 0: the search mask was empty                                             */
+    int32_t n;          /* pixels in the search mask, saturating once >= 64 were seen               */
+    int32_t reserved;
+} psam_neg_point;
+
+/* get_sam_input_points(..., get_neg_points=True, l=1) (models/ProtoSAM.py:361-434).  For image i, neg[i][r] (r < n_rec)
+ * is the most confident background pixel in the ring cv2.dilate(component r, 3x3, iterations=ring_width) minus the
+ * component, and neg[i][max_cc] the most confident pixel of the whole image with p_bg >= thresh; "most confident" is
+ * torch.topk(values[mask], 1) with its tie rules.  The caller stacks [ring point, global point] per component.
+ *   labels    [n_img,out,out] as written by psam_components (0/1 image of the kept component with use_cca)
+ *   p_bg      background probabilities, image i at p_bg + i * p_bg_image_stride (= channel 0 of probs2)
+ *   host_aliasing != 0: the ring search reads the map thresholded in place (p_bg < thresh -> 0), which is what the
+ *   reference computes when its tensors live on the CPU (.cpu() returns a view, models/ProtoSAM.py:363-364 vs :414);
+ *   0 = the raw map, as on the reference's CUDA path.  out <= 1024. */
+int psam_neg_points(const int32_t* labels, const float* p_bg, int64_t p_bg_image_stride, const psam_image_hdr* hdr,
+                    const psam_prompt_rec* recs, int n_img, int out, int max_cc, int use_cca, int ring_width, float thresh,
+                    int host_aliasing, psam_neg_point* neg /* [n_img, max_cc + 1] */, psam_stream_t stream);
+
+/* get_sam_input_mask + the mask_input of predict_w_masks (models/ProtoSAM.py:452-476): per component the 0/1 mask
+ * resized to size x size (cv2.INTER_NEAREST), foreground 10, background -8 cast to uint8 (= 248).  Masks are packed in
+ * image order: masks[offsets[i] + r] belongs to component r of image i; offsets [n_img + 1] is written here; masks
+ * beyond `capacity` are dropped (offsets[n_img] tells). */
+int psam_mask_prompts(const int32_t* labels, const psam_image_hdr* hdr, const psam_prompt_rec* recs, int n_img, int out,
+                      int max_cc, int use_cca, int size, int capacity, uint8_t* masks /* [capacity,size,size] */,
+                      int32_t* offsets, psam_stream_t stream);
+
+/* get_confidence_from_logits (util/utils.py:429-434, ProtoSAM coarse_pred_only :580-590) from foreground probabilities
+ * p_fg [n_img, pixels_per_image] (psam_upsample_softmax, fg_only = 0): conf[i] = sum(p[p >= 0.5]) / (count + 1e-6). */
+int psam_confidence(const float* p_fg, int n_img, int64_t pixels_per_image, double* conf, psam_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -182,6 +182,40 @@ def gen_alp_config_shapes():
     print("alp_configs:", len(names), "cases")
 
 
+def gen_alp_config_shapes2():
+    """The remaining BASELINE shapes (configs 3, 4 and the window sweep of config 5 at C = 1024), one query slice each.
+    Only the small outputs are stored (maps, survival masks, assignments): the prototype rows of these shapes would
+    add tens of MB to the repository and are already pinned at C <= 768 by alp_configs.npz."""
+    store = {"versions": _versions()}
+    names = []
+    jobs = []      # (key, cfg-like dict, seed, L, ws, [(kind, mode)])
+    c3 = synth.CONFIGS["cfg3_synapse_ct"]
+    jobs.append(("cfg3_synapse_ct", c3, 1234, 2, c3["ws"], [("bg", "gridconv"), ("fg", "gridconv+"), ("fgmask", "mask")]))
+    c4 = synth.CONFIGS["cfg4_polyp_1024"]
+    jobs.append(("cfg4_polyp_1024", c4, 1234, 1, c4["ws"], [("bg", "gridconv"), ("fg", "gridconv+"), ("fgmask", "mask")]))
+    c5 = synth.CONFIGS["cfg5_stress_vitl"]
+    for ws in (3, 6, 7):
+        jobs.append((f"cfg5_ws{ws}", c5, 50 + ws, 1, ws, [("bg", "gridconv"), ("fg", "gridconv+")]))
+    for key, cfg, seed, L, ws, kinds in jobs:
+        vol = synth.make_volume(seed, Q=1, L=L, C=cfg["C"], h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+        sup_x = torch.from_numpy(vol.sup).permute(0, 3, 1, 2)[None, :, None]
+        qry = torch.from_numpy(vol.qry[0]).permute(2, 0, 1)[None, None]
+        for l in range(L):
+            for kind, mode in kinds:
+                mask = vol.bg[l] if kind == "bg" else vol.fg[l]
+                out = run_ref_alp(qry, sup_x, torch.from_numpy(mask)[None, :, None], mode, 0.95, [8, 8],
+                                  [cfg["h"], cfg["w"]], True, ws, vis_sim=False)
+                n = f"{key}/l{l}/q0/{kind}"
+                names.append(n)
+                for k in ("pred_grid", "debug_assign", "survive"):
+                    if k in out:
+                        store[f"{n}/{k}"] = out[k]
+        store[f"{key}/meta"] = np.array([seed, 1, L, ws])
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "alp_configs2.npz"), **store)
+    print("alp_configs2:", len(names), "cases")
+
+
 # ------------------------------------------------------------------ prompts
 
 def run_ref_protosam(logits_S, use_cca, point_mode, S):
@@ -261,13 +295,102 @@ def gen_prompts():
     print("prompts:", len(names), "cases")
 
 
+# ------------------------------------------------------------------ optional variants
+
+def variant_cases():
+    cases = {n: (low, S) for n, low, S in prompt_cases()}
+    return [(n,) + cases[n] for n in ("blobs_32_256", "smooth_32_256", "smooth_37_518", "speckle_32_256",
+                                      "saturated_37_518", "empty_24_256")]
+
+
+def gen_variants():
+    """Negative points, mask prompts, coarse_pred_only confidence (models/ProtoSAM.py:361-434, 452-498, 580-590) and
+    the ProtoMedSAM box path (models/ProtoMedSAM.py:175-200), all through the reference's own forward()."""
+    _, PS, uu = ref_shims.load_pipeline()
+    PM = ref_shims.load_protomedsam()
+    store = {"versions": _versions()}
+    names = []
+    for name, low, S in variant_cases():
+        low_t = torch.from_numpy(low)
+        logits_S = F.interpolate(low_t, size=(S, S), mode="bilinear")
+        store[f"{name}/low"] = low
+        store[f"{name}/S"] = np.array(S)
+        names.append(name)
+        img = torch.from_numpy(synth.uniform(77, (1, 3, S, S)))
+
+        def run(device_semantics=False, **kw):
+            with _quiet():
+                model = PS.ProtoSAM(image_size=(1024, 1024), coarse_segmentation_model=ref_shims.FixedLogitsCoarseModel(logits_S),
+                                    num_points_for_sam=1, **kw)
+            model.eval()
+            ctx = ref_shims.device_copy_semantics() if device_semantics else contextlib.nullcontext()
+            with torch.no_grad(), _quiet(), ctx:
+                pred, scores = model(img, ref_shims._NullInput(), degrees_rotate=0)
+            return model.predictor.calls, pred, scores
+
+        # negative points, both .cpu() semantics
+        for dev_sem in (False, True):
+            for use_cca in (False, True):
+                calls, _, _ = run(dev_sem, use_points=True, use_bbox=True, use_cca=use_cca, point_mode="both",
+                                  use_neg_points=True)
+                key = f"{name}/neg_dev{int(dev_sem)}_cca{int(use_cca)}"
+                store[f"{key}/ncalls"] = np.array(len(calls))
+                if calls:
+                    # every call has 2 positive + up to 2 negative points; pad to 4 rows with -1
+                    pts = np.full((len(calls), 4, 2), -1.0)
+                    lab = np.full((len(calls), 4), -1, np.int64)
+                    for i, c in enumerate(calls):
+                        pts[i, : len(c["point_coords"])] = c["point_coords"]
+                        lab[i, : len(c["point_labels"])] = c["point_labels"]
+                    store[f"{key}/points"] = pts
+                    store[f"{key}/point_labels"] = lab
+        # mask prompts
+        calls, _, _ = run(False, use_points=False, use_bbox=False, use_mask=True, use_cca=False, point_mode="both")
+        mcalls = [c for c in calls if c.get("mask_input") is not None]
+        store[f"{name}/mask/ncalls"] = np.array(len(mcalls))
+        if mcalls:
+            m = np.stack([c["mask_input"] for c in mcalls])              # [ncc,1,256,256] uint8
+            store[f"{name}/mask/values"] = np.unique(m)
+            store[f"{name}/mask/fg_bits"] = np.packbits(m == 10)
+            store[f"{name}/mask/dtype"] = np.array(str(m.dtype))
+        # coarse_pred_only: confidence (+ cca)
+        for use_cca in (False, True):
+            _, pred, scores = run(False, use_points=True, use_bbox=True, use_cca=use_cca, point_mode="both",
+                                  coarse_pred_only=True)
+            store[f"{name}/coarse_cca{int(use_cca)}/conf"] = np.array(float(scores[0]))
+            store[f"{name}/coarse_cca{int(use_cca)}/pred_bits"] = np.packbits(np.asarray(pred).astype(np.uint8))
+        # ProtoMedSAM: boxes handed to medsam_inference, and the confidences its cca() sees
+        for use_cca in (False, True):
+            with _quiet():
+                med = PM.ProtoMedSAM(image_size=(1024, 1024),
+                                     coarse_segmentation_model=ref_shims.FixedLogitsCoarseModel(logits_S), use_cca=use_cca)
+            med.eval()
+            with torch.no_grad(), _quiet():
+                med(img, ref_shims._NullInput(), degrees_rotate=0)
+            key = f"{name}/medsam_cca{int(use_cca)}"
+            store[f"{key}/ncalls"] = np.array(len(med.captured_boxes))
+            if med.captured_boxes:
+                store[f"{key}/boxes"] = med.captured_boxes[0]
+        lg = F.interpolate(logits_S, size=(1024, 1024), mode="bilinear")
+        P = lg.softmax(1)                                                # what ProtoMedSAM hands to cca() after need_softmax
+        store[f"{name}/medsam_need_softmax"] = np.array(bool(uu.need_softmax(lg)))
+        pred = np.array(P.argmax(1)[0])
+        _, conf = uu.get_connected_components(pred, P, return_conf=True)
+        store[f"{name}/medsam_conf"] = np.array([float(conf[k]) for k in sorted(conf)])
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "variants.npz"), **store)
+    print("variants:", len(names), "cases")
+
+
 def main():
     assert ref_shims.reference_available(), "reference tree not mounted"
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(1234)
     gen_alp_small()
     gen_alp_config_shapes()
+    gen_alp_config_shapes2()
     gen_prompts()
+    gen_variants()
 
 
 if __name__ == "__main__":

@@ -353,3 +353,124 @@ def coarse_to_prompts(low_logits, mid_size, out_size=1024, use_cca=False, point_
     out["bboxes"] = get_bbox_per_cc(cc)
     out["points"], out["point_labels"] = get_sam_input_points(cc, p_fg, point_mode)
     return out
+
+
+# --------------------------------------------------------------------------
+# F. ProtoMedSAM variant -- models/ProtoMedSAM.py:175-200
+# --------------------------------------------------------------------------
+
+def need_softmax(x, dim=1):
+    """util/utils.py:62-63: ``not all(isclose(x.sum(dim), 1) & (x >= 0))`` (the [N,H,W] sum test broadcasts against
+    the [N,2,H,W] sign test)."""
+    x = np.asarray(x, dtype=np.float32)
+    s = x.sum(axis=dim, dtype=np.float32)
+    close = np.isclose(s, np.ones_like(s))          # torch.isclose defaults: rtol=1e-5, atol=1e-8, as numpy
+    return not bool(np.all(np.expand_dims(close, dim) & (x >= 0)))
+
+
+def coarse_to_prompts_medsam(low_logits, mid_size, out_size=1024, use_cca=False, image_size=(1024, 1024)):
+    """ProtoMedSAM.forward lines 175-200 for one query slice and one label.
+
+    The coarse logits are turned into probabilities FIRST when ``need_softmax`` says so (:178-179); the mask is
+    their argmax; ``cca`` / ``get_connected_components`` then apply ``softmax(1)`` to those probabilities AGAIN
+    (util/utils.py:486), so the per-component confidences -- and with ``use_cca`` the component kept -- are those of
+    a softmax of a softmax.  Boxes are ``get_bbox_per_cc / [W,H,W,H] * max(image_size)`` in float64 (:197-198)."""
+    logits, p, _ = coarse_logits_to_probs(low_logits, mid_size, out_size)
+    output = p if need_softmax(logits) else logits
+    pred = (output[0, 1] > output[0, 0]).astype(np.uint8)            # argmax over two classes keeps class 0 on ties
+    conf_p = softmax2(output)[0, 1]
+    if use_cca:
+        cc = cca(pred, conf_p, return_cc=True)
+        conf = None
+    else:
+        cc, conf = get_connected_components(pred, conf_p, return_conf=True)
+    out = dict(pred=pred, conf_p=conf_p, n=cc[0], labels=cc[1], stats=cc[2], centroids=cc[3], conf=conf,
+               empty=bool(pred.max() == 0), need_softmax=need_softmax(logits))
+    if out["empty"]:
+        return out
+    H = W = out_size
+    out["bboxes"] = get_bbox_per_cc(cc)
+    out["boxes_1024"] = out["bboxes"] / np.array([W, H, W, H]) * max(image_size)
+    return out
+
+
+# --------------------------------------------------------------------------
+# G. optional prompt variants -- models/ProtoSAM.py:361-434, 452-498, 580-590
+# --------------------------------------------------------------------------
+
+def get_confidence_from_logits(logits):
+    """util/utils.py:429-434 (``coarse_pred_only``): mean foreground probability over the pixels with p >= 0.5.
+    The reference sums in float32 (ATen's vectorised cascade); the sums here are float64, so compare at ~1e-6."""
+    p = softmax2(np.asarray(logits, dtype=np.float32))[0, 1].astype(np.float64).ravel()
+    sel = p >= 0.5
+    return float(p[sel].sum() / (sel.sum() + 1e-6))
+
+
+def dilate_square(mask, iterations=10):
+    """cv2.dilate(mask, np.ones((3,3)), iterations=n): n passes of a 3x3 maximum = one (2n+1)^2 maximum clipped at the
+    image border (Chebyshev distance <= n)."""
+    m = np.asarray(mask).astype(bool)
+    out = m.copy()
+    for _ in range(iterations):
+        nxt = out.copy()
+        nxt[1:, :] |= out[:-1, :]; nxt[:-1, :] |= out[1:, :]
+        out = nxt
+        nxt = out.copy()
+        nxt[:, 1:] |= out[:, :-1]; nxt[:, :-1] |= out[:, 1:]
+        out = nxt
+    return out
+
+
+def _topk1_masked(values, mask):
+    """get_most_conf_points(values, mask, 1) (models/ProtoSAM.py:266-289): (x, y) of torch.topk(values[mask], 1), or
+    None when the mask is empty."""
+    L = lib()
+    ys, xs = np.nonzero(mask)
+    if len(ys) == 0:
+        return None
+    v = _f32(values[ys, xs])
+    pos = L.psamo_topk1_pos(_ptr(v), int(len(v)))
+    return np.array([[xs[pos], ys[pos]]], dtype=np.int64)
+
+
+def get_neg_points(cc, output_p, l=1, host_aliasing=True, thresh=0.95, iterations=10):
+    """The negative points of ``get_sam_input_points(..., get_neg_points=True)`` (models/ProtoSAM.py:361-434) for
+    l = 1: per component, vstack([most confident background point in the ring of Chebyshev width 10 around the
+    component, most confident background point of the image with p_bg >= 0.95]).
+
+    ``host_aliasing``: on a CPU tensor ``output_p[0, 0].detach().cpu()`` is a VIEW, so the in-place thresholding at
+    :364 (``bg_p[bg_p < 0.95] = 0``) also zeroes the map the ring search reads at :414 -- that is what the CPU-generated
+    fixtures contain; on the reference's CUDA path ``.cpu()`` copies and the ring search sees the raw p_bg
+    (host_aliasing=False)."""
+    assert l == 1
+    p_bg = _f32(output_p[0, 0])
+    thr = np.where(p_bg < np.float32(thresh), np.float32(0), p_bg)
+    glob = _topk1_masked(thr, thr > 0)
+    ring_src = thr if host_aliasing else p_bg
+    out = []
+    for cid in [int(i) for i in np.unique(cc[1]) if i != 0]:
+        comp = cc[1] == cid
+        ring = dilate_square(comp, iterations) & ~comp
+        neg = _topk1_masked(ring_src, ring)
+        if neg is not None and glob is not None:
+            neg = np.vstack([neg, glob])
+        else:
+            neg = glob if neg is None else neg
+        out.append(neg)
+    return out
+
+
+def sam_mask_inputs(cc, size=256):
+    """get_sam_input_mask + predict_w_masks (models/ProtoSAM.py:452-498): per component the 0/1 mask resized to
+    256x256 with cv2.INTER_NEAREST (source index = min(floor(dst * src/dst), src-1)), foreground -> 10, background
+    -> -8, handed to SamPredictor.predict as ``mask_input = in_mask[None].astype(np.uint8)`` (-8 wraps to 248).
+    Returns (uint8 [ncc,1,size,size], labels [ncc])."""
+    ids = [int(i) for i in np.unique(cc[1]) if i != 0]
+    H, W = cc[1].shape
+    # cv2 resizeNN: sx = min(cvFloor(x * ifx), src - 1) with ifx = 1 / inv_scale_x, inv_scale_x = (double)dst / src
+    ys = np.minimum(np.floor(np.arange(size) * (1.0 / (size / H))).astype(np.int64), H - 1)
+    xs = np.minimum(np.floor(np.arange(size) * (1.0 / (size / W))).astype(np.int64), W - 1)
+    small = cc[1][ys[:, None], xs[None, :]]
+    masks = np.stack([np.where(small == cid, 10, 248).astype(np.uint8)[None] for cid in ids]) if ids else \
+        np.zeros((0, 1, size, size), np.uint8)
+    return masks, np.array(ids)

@@ -103,7 +103,7 @@ class CapturingPredictor:
 
     def predict(self, **kw):
         self.calls.append({k: (None if v is None else np.array(v)) if k in
-                           ("point_coords", "point_labels", "box") else v
+                           ("point_coords", "point_labels", "box", "mask_input") else v
                            for k, v in kw.items()})
         h, w = self.image.shape[:2]
         return (np.zeros((1, h, w), dtype=bool), np.ones((1,), dtype=np.float32), None)
@@ -139,6 +139,53 @@ def load_pipeline():
         PS.ProtoSAM.get_sam = get_sam
         _PIPE = (gpf, PS, uu)
     return _PIPE
+
+
+_MED = None
+
+
+def load_protomedsam():
+    """models/ProtoMedSAM.py with the MedSAM network replaced by a stub: ``medsam_inference`` records the boxes it is
+    handed (the end of the path this repo owns) and returns an empty mask, so no checkpoint is needed."""
+    global _MED
+    if _MED is None:
+        load_pipeline()
+        PM = importlib.import_module("models.ProtoMedSAM")
+
+        class _Enc(nn.Module):
+            def forward(self, x):
+                return torch.zeros(1, 256, 64, 64)
+
+        class _Med(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.image_encoder = _Enc()
+
+        def get_sam(self, checkpoint_path):
+            self.medsam = _Med()
+            self.captured_boxes = []
+
+        def medsam_inference(self, img_embed, box_1024, H, W, query_label=None):
+            self.captured_boxes.append(np.array(box_1024))
+            return np.zeros((H, W), np.uint8), 1.0
+
+        PM.ProtoMedSAM.get_sam = get_sam
+        PM.ProtoMedSAM.medsam_inference = medsam_inference
+        _MED = PM
+    return _MED
+
+
+@contextlib.contextmanager
+def device_copy_semantics():
+    """On the reference's CUDA path ``tensor.cpu()`` COPIES; on a CPU tensor it returns the tensor itself, so in-place
+    edits of the result alias the source (models/ProtoSAM.py:363-364 vs :414).  Inside this context ``.cpu()`` clones,
+    which reproduces what the CUDA path computes."""
+    orig = torch.Tensor.cpu
+    torch.Tensor.cpu = lambda self, *a, **k: self.clone()
+    try:
+        yield
+    finally:
+        torch.Tensor.cpu = orig
 
 
 class FixedLogitsCoarseModel:

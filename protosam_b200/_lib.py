@@ -18,8 +18,11 @@ MODE_IDS = {"mask": MODE_MASK, "gridconv": MODE_GRIDCONV, "gridconv+": MODE_GRID
 MODE_NAMES = {v: k for k, v in MODE_IDS.items()}
 
 SET_EMPTY = 1
+ABI_VERSION = 2
+PROB_SOFTMAX, PROB_SOFTMAX_TWICE = 0, 1
 IMG_EMPTY, IMG_RUN_OVERFLOW, IMG_CC_TRUNCATED, IMG_CCA_AMBIGUOUS = 1, 2, 4, 8
 REC_SELECTED = 1
+PACKED_OVERFLOW = 1
 
 c_p = ctypes.c_void_p
 c_i = ctypes.c_int
@@ -47,12 +50,17 @@ SIGNATURES = {
     "psam_alp_match": (c_i, [c_p, c_i64, c_i64, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p,
                              c_p, c_sz, c_i, c_p]),
     "psam_upsample_workspace": (c_sz, [c_i, c_i]),
-    "psam_upsample_softmax": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_sz, c_p]),
+    "psam_upsample_softmax": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_sz, c_p]),
     "psam_prompts_workspace": (c_sz, [c_i] * 4),
     "psam_components": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "psam_records_to_sam": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "psam_coarse_to_prompts_workspace": (c_sz, [c_i] * 4),
-    "psam_coarse_to_prompts": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    "psam_coarse_to_prompts": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    "psam_packed_bytes": (c_sz, [c_i, c_i]),
+    "psam_compact_records": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "psam_neg_points": (c_i, [c_p, c_p, c_i64, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
+    "psam_mask_prompts": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "psam_confidence": (c_i, [c_p, c_i, c_i64, c_p, c_p]),
 }
 
 _lib = None
@@ -72,7 +80,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.psam_abi_version() != 1:
+    if lib.psam_abi_version() != ABI_VERSION:
         raise RuntimeError("protosam_b200: ABI version mismatch between _lib.py and libpsam_b200.so")
     _lib = lib
     return lib

@@ -21,6 +21,16 @@ void prof_end(const char* what, cudaStream_t stream);
         if (psam::g_profiling) psam::prof_begin(stream); \
     } while (0)
 
+// Every kernel of the library asks for the maximum shared-memory carveout (once per kernel and device): CTAs of two
+// kernels whose L1/shared splits differ cannot be resident on one SM at the same time, and the pipeline relies on the
+// ALU-bound prompt kernels of one volume running beside the tensor-bound GEMM CTA of the next.
+void max_carveout_once(const void* kernel, bool* done_per_device);
+#define PSAM_MAX_CARVEOUT(kernel)                                                     \
+    do {                                                                              \
+        static bool done__[64] = {};                                                  \
+        psam::max_carveout_once(reinterpret_cast<const void*>(kernel), done__);       \
+    } while (0)
+
 #define PSAM_CHECK_ARG(cond, ...)                     \
     do {                                              \
         if (!(cond)) {                                \

@@ -16,7 +16,10 @@
 //
 // Roofline: latency/HBM bound, small: algorithmic bytes per image = out^2/8 (bits) + 4*n_fg
 // (p_fg under the mask) read + 96*ncc written.
+#include <cstring>
+
 #include "psam_common.cuh"
+#include "psam_topk.cuh"
 
 namespace psam {
 
@@ -81,60 +84,6 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     lo = __shfl_xor_sync(0xffffffffu, lo, o);
     hi = __shfl_xor_sync(0xffffffffu, hi, o);
     return ((unsigned long long)hi << 32) | lo;
-}
-
-// torch.topk(v, 1) for n < 64: libstdc++ nth_element replayed (oracle: psamo_topk1_pos).
-struct TK { float v; int i; };
-__device__ __forceinline__ void tk_swap(TK& a, TK& b) { TK t = a; a = b; b = t; }
-
-__device__ int topk1_small(TK* q, int n)
-{
-    int first = 0, last = n;
-    int depth = 0;
-    for (int m = n; m > 1; m >>= 1) ++depth;
-    depth *= 2;
-    while (last - first > 3) {
-        if (depth == 0) {
-            for (int i = first + 1; i < last; ++i)
-                if (q[i].v > q[first].v) tk_swap(q[i], q[first]);
-            return q[0].i;
-        }
-        --depth;
-        const int mid = first + (last - first) / 2;
-        {   // __move_median_to_first(first, first+1, mid, last-1)
-            TK &r = q[first], &a = q[first + 1], &b = q[mid], &c = q[last - 1];
-            if (a.v > b.v) {
-                if (b.v > c.v) tk_swap(r, b);
-                else if (a.v > c.v) tk_swap(r, c);
-                else tk_swap(r, a);
-            } else if (a.v > c.v) tk_swap(r, a);
-            else if (b.v > c.v) tk_swap(r, c);
-            else tk_swap(r, b);
-        }
-        int f = first + 1, l = last;   // __unguarded_partition(first+1, last, pivot=first)
-        for (;;) {
-            while (q[f].v > q[first].v) ++f;
-            --l;
-            while (q[first].v > q[l].v) --l;
-            if (!(f < l)) break;
-            tk_swap(q[f], q[l]);
-            ++f;
-        }
-        if (f <= 0) first = f; else last = f;   // nth == position 0
-    }
-    // __insertion_sort(first, last)
-    for (int i = first + 1; i < last; ++i) {
-        TK val = q[i];
-        if (val.v > q[first].v) {
-            for (int k = i; k > first; --k) q[k] = q[k - 1];
-            q[first] = val;
-        } else {
-            int cur = i, next = i - 1;
-            while (val.v > q[next].v) { q[cur] = q[next]; cur = next; --next; }
-            q[cur] = val;
-        }
-    }
-    return q[0].i;
 }
 
 // Exact statistics of one foreground run [s,e] of row y, computed by a whole warp:
@@ -559,38 +508,79 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
         }
         __syncthreads();
 
-        // ---- S12/S13: records (label order); small components replay torch.topk's nth_element
+        // ---- S12: records (label order) ------------------------------------------------------------
         for (int r = tid; r < n_rec; r += CT) {
             const Acc a = acc[r];
             psam_prompt_rec rec;
             rec.box[0] = a.minx; rec.box[1] = a.miny; rec.box[2] = a.maxx; rec.box[3] = a.maxy;
-            unsigned int idx = 0xFFFFFFFFu - (unsigned int)(a.best & 0xFFFFFFFFu);
-            float pbest = __uint_as_float((unsigned int)(a.best >> 32));
-            if (a.area < 64) {
-                TK q[64];
-                int n = 0;
-                for (unsigned int y = a.miny; y <= a.maxy; ++y)
-                    for (int j = s_rowstart[y]; j < s_rowstart[y + 1]; ++j)
-                        if (parent[j] == a.root)
-                            for (int x = run_s[j]; x <= (int)run_e[j]; ++x) {
-                                q[n].v = pfg[(size_t)y * out + x];
-                                q[n].i = (int)(y * out + x);
-                                ++n;
-                            }
-                idx = (unsigned int)topk1_small(q, n);
-                pbest = pfg[idx];
-            }
+            const unsigned int idx = 0xFFFFFFFFu - (unsigned int)(a.best & 0xFFFFFFFFu);
             rec.conf_pt[0] = idx % out;
             rec.conf_pt[1] = idx / out;
             rec.centroid[0] = (double)a.sumx / (double)a.area;
             rec.centroid[1] = (double)a.sumy / (double)a.area;
             rec.conf = ((double)a.sump * (1.0 / 16777216.0)) / ((double)n_fg + 1e-6);
-            rec.conf_pt_p = pbest;
+            rec.conf_pt_p = __uint_as_float((unsigned int)(a.best >> 32));
             rec.area = (int)a.area;
             rec.label = rank[a.root] + 1;
             rec.flags = P.use_cca ? PSAM_REC_SELECTED : 0;
+            rec.reserved[0] = rec.reserved[1] = 0;
             recs[r] = rec;
             if (P.use_cca) hdr->selected = rec.label;
+        }
+        if (tid == 0) s_misc[9] = 0;
+        __syncthreads();
+        // ---- S13: components of < 64 pixels: torch.topk(v, 1) takes its nth_element path there, which on TIES of
+        // the maximum does not return the first pixel in raster order.  One warp per such component gathers the
+        // component's pixels in raster order (lane = candidate pixel of the bounding box, membership = the run
+        // under it belongs to the component) and, only if the maximum is attained more than once, replays
+        // libstdc++'s nth_element on them.  A unique maximum needs no replay: every algorithm returns it.
+        {
+            TK* q = reinterpret_cast<TK*>(s_prefix) + wid * 64;         // s_prefix is free again: 32 warps x 64 x 8 B = 16 KB
+            for (int r = wid; r < n_rec; r += CT / 32) {
+                const Acc a = acc[r];
+                if (a.area >= 64) continue;
+                const int bwid = (int)(a.maxx - a.minx) + 1, bh = (int)(a.maxy - a.miny) + 1, ncand = bwid * bh;
+                int n = 0;
+                for (int c0 = 0; c0 < ncand && n < (int)a.area; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool in = false;
+                    int x = 0, y = 0;
+                    if (c < ncand) {
+                        y = (int)a.miny + c / bwid;
+                        x = (int)a.minx + c % bwid;
+                        if ((bits[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u) {
+                            int l = s_rowstart[y], rr = s_rowstart[y + 1];   // the run of row y that ends at or after x
+                            while (l < rr) {
+                                const int m = (l + rr) >> 1;
+                                if ((int)run_e[m] < x) l = m + 1; else rr = m;
+                            }
+                            in = parent[l] == a.root;
+                        }
+                    }
+                    const uint32_t inb = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int pos = n + __popc(inb & ((1u << lane) - 1u));
+                        q[pos].v = pfg[(size_t)y * out + x];
+                        q[pos].i = y * out + x;
+                    }
+                    n += __popc(inb);
+                }
+                __syncwarp();
+                float vmax = -1.0f;
+                for (int i = lane; i < n; i += 32) vmax = fmaxf(vmax, q[i].v);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                int ties = 0;
+                for (int i = lane; i < n; i += 32) ties += q[i].v == vmax;
+                ties = warp_sum_i(ties);
+                if (ties > 1 && lane == 0) {
+                    const int idx = topk1_small(q, n);
+                    recs[r].conf_pt[0] = idx % out;
+                    recs[r].conf_pt[1] = idx / out;
+                    recs[r].conf_pt_p = pfg[idx];
+                }
+                __syncwarp();
+            }
         }
         if (tid == 0) {
             hdr->ncc = ncc;
@@ -651,9 +641,90 @@ __global__ void __launch_bounds__(256) k_records_to_sam(const psam_image_hdr* __
     bx[3] = (float)((double)rec.box[3] * sy);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Records of a batch, compacted: what leaves the GPU (gather to rank 0, device->host copy).  The dense layout
+// [n_img, max_cc] is >95 % empty slots (1-3 components per image, max_cc = 256); here the headers are followed by the
+// live records only, in image order.  One CTA: exclusive scan of n_rec over the images, then one warp per image copies
+// its records (96 B = 6 x 16 B per lane).
+//   packed = [n_alloc headers (64 B each; hdr.reserved = index of the image's first record)]
+//            [psam_packed_tail: total records, capacity, flags]  [capacity records]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_compact_records(const psam_image_hdr* __restrict__ hdr,
+                                                          const psam_prompt_rec* __restrict__ recs, int n_img, int n_alloc,
+                                                          int max_cc, int capacity, uint8_t* __restrict__ packed)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    psam_image_hdr* ohdr = reinterpret_cast<psam_image_hdr*>(packed);
+    psam_packed_tail* tail = reinterpret_cast<psam_packed_tail*>(packed + (size_t)n_alloc * sizeof(psam_image_hdr));
+    psam_prompt_rec* orec = reinterpret_cast<psam_prompt_rec*>(tail + 1);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_alloc; i0 += 1024) {
+        const int i = i0 + tid;
+        psam_image_hdr h;
+        if (i < n_img) h = hdr[i];
+        else memset(&h, 0, sizeof(h));
+        const int n = i < n_img ? h.n_rec : 0;
+        const int ex = warp_excl_scan_i(n, lane);
+        if (lane == 31) s_warp[wid] = ex + n;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int k = 0; k < 32; ++k) {
+            const int v = s_warp[k];
+            if (k < wid) woff += v;
+            tot += v;
+        }
+        const int first = s_base + woff + ex;
+        if (i < n_alloc) {
+            h.reserved = first;
+            ohdr[i] = h;
+        }
+        // one warp per image of this chunk copies the image's records
+        for (int j = 0; j < 32; ++j) {
+            const int img = i0 + wid * 32 + j;
+            const int nj = __shfl_sync(0xffffffffu, n, j), fj = __shfl_sync(0xffffffffu, first, j);
+            const uint4* src = reinterpret_cast<const uint4*>(recs + (size_t)img * max_cc);
+            uint4* dst = reinterpret_cast<uint4*>(orec + fj);
+            for (int k = lane; k < nj * 6; k += 32)
+                if (fj + k / 6 < capacity) dst[k] = src[k];
+        }
+        __syncthreads();
+        if (tid == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        tail->total = s_base;
+        tail->capacity = capacity;
+        tail->flags = s_base > capacity ? PSAM_PACKED_OVERFLOW : 0;
+        tail->n_img = n_img;
+        for (int k = 0; k < 12; ++k) tail->reserved[k] = 0;
+    }
+}
+
 }  // namespace psam
 
 using namespace psam;
+
+extern "C" size_t psam_packed_bytes(int n_alloc, int capacity)
+{
+    if (n_alloc <= 0 || capacity < 0) return 0;
+    return (size_t)n_alloc * sizeof(psam_image_hdr) + sizeof(psam_packed_tail) + (size_t)capacity * sizeof(psam_prompt_rec);
+}
+
+extern "C" int psam_compact_records(const psam_image_hdr* hdr, const psam_prompt_rec* recs, int n_img, int n_alloc, int max_cc,
+                                    int capacity, void* packed, psam_stream_t stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(hdr && recs && packed, "psam_compact_records: null pointer");
+    PSAM_CHECK_ARG(n_img >= 1 && n_alloc >= n_img && max_cc >= 1 && capacity >= 1, "psam_compact_records: bad shape");
+    PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_compact_records);
+    k_compact_records<<<1, 1024, 0, stream>>>(hdr, recs, n_img, n_alloc, max_cc, capacity, static_cast<uint8_t*>(packed));
+    PSAM_CHECK_LAUNCH("k_compact_records");
+    return PSAM_OK;
+}
 
 static int comp_grid(int n_img)
 {
@@ -725,6 +796,7 @@ extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, cons
         attr_done = true;
     }
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_components);
     k_components<<<ctas, CT, dyn, stream>>>(P);
     PSAM_CHECK_LAUNCH("k_components");
     return PSAM_OK;
@@ -743,7 +815,7 @@ extern "C" size_t psam_coarse_to_prompts_workspace(int n_img, int out, int max_r
 }
 
 extern "C" int psam_coarse_to_prompts(const float* logits, int n_img, int h, int w, int mid, int out, int use_cca,
-                                      int max_cc, int max_runs, psam_image_hdr* hdr, psam_prompt_rec* recs,
+                                      int prob_mode, int max_cc, int max_runs, psam_image_hdr* hdr, psam_prompt_rec* recs,
                                       void* workspace, size_t workspace_bytes, psam_stream_t stream)
 {
     PSAM_CHECK_ARG(workspace, "psam_coarse_to_prompts: null workspace");
@@ -758,7 +830,7 @@ extern "C" int psam_coarse_to_prompts(const float* logits, int n_img, int h, int
     const size_t upw = psam_upsample_workspace(n_img, out);
     char* upws = cv.take<char>(upw);
     char* rest = static_cast<char*>(workspace) + cv.used();
-    int rc = psam_upsample_softmax(logits, n_img, h, w, mid, out, p_fg, bits, nullptr, wstat, 1, upws, upw, stream);
+    int rc = psam_upsample_softmax(logits, n_img, h, w, mid, out, p_fg, bits, nullptr, wstat, 1, prob_mode, upws, upw, stream);
     if (rc) return rc;
     return psam_components(bits, p_fg, wstat, n_img, out, use_cca, max_cc, max_runs, hdr, recs, nullptr, rest,
                            workspace_bytes - cv.used(), stream);
@@ -777,6 +849,7 @@ extern "C" int psam_records_to_sam(const psam_image_hdr* hdr, const psam_prompt_
     const int new_h = (int)((double)old_h * scale + 0.5), new_w = (int)((double)old_w * scale + 0.5);
     const double sx = (double)new_w / (double)old_w, sy = (double)new_h / (double)old_h;
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_records_to_sam);
     k_records_to_sam<<<(n_img * max_cc + 255) / 256, 256, 0, stream>>>(hdr, recs, n_img, max_cc, point_mode, sx, sy, points,
                                                                        labels, boxes);
     PSAM_CHECK_LAUNCH("k_records_to_sam");

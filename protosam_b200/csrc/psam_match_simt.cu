@@ -191,6 +191,7 @@ int launch_match_simt(const MatchParams& p, cudaStream_t stream)
 {
     dim3 grid((p.HW + BM - 1) / BM, p.nsets, p.Q);
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_match_simt);
     k_match_simt<<<grid, 256, 0, stream>>>(p);
     PSAM_CHECK_LAUNCH("k_match_simt");
     return PSAM_OK;

@@ -654,6 +654,7 @@ static int launch_gemm(const tc::TcParams& t, int grid, cudaStream_t stream)
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT((k_match_tc<kFused, kStages>));
     k_match_tc<kFused, kStages><<<grid, kFused ? THREADS_FUSED : THREADS, smem_bytes(kStages), stream>>>(t);
     PSAM_CHECK_LAUNCH(kFused ? "k_match_tc_fused" : "k_match_tc");
     return PSAM_OK;
@@ -694,11 +695,13 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     float* scale = fused ? nullptr : reinterpret_cast<float*>(a_img + align_up(L.a_bytes, 1024));
 
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_pack_protos);
     k_pack_protos<<<dim3(pad16(p.cap_rows) / 8, p.nsets), 256, 0, stream>>>(p.protos, p.cap_rows, p.counts, p.C, L.KB, L.G,
                                                                            b_img);
     PSAM_CHECK_LAUNCH("k_pack_protos");
     if (!fused) {
         PSAM_PROF_BEGIN(stream);
+        PSAM_MAX_CARVEOUT(k_pack_query);
         k_pack_query<<<L.ntiles * BM / 8, 256, 0, stream>>>(p.qry, p.slice_stride, p.row_stride, p.HW, L.R, p.C, L.KB,
                                                            a_img, scale);
         PSAM_CHECK_LAUNCH("k_pack_query");

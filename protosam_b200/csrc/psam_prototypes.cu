@@ -24,16 +24,16 @@ struct SetModes {
 // ------------------------------------------------------------------------------------
 // K1a: per set -- window mask fractions (exact ATen order: sequential (dy,dx) sum, true
 // division), AUTO_FG decision, survive flags, ordered row indices, per-shot mask sums.
-// grid = nsets, block = 256.
+// One CTA of 256 threads per set (CTA 0 of each set's row in k_proto_stage1).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pool_mask(const float* __restrict__ sup_y, SetModes modes, int S, int h,
+__device__ __forceinline__ void pool_mask_body(int set, const float* __restrict__ sup_y, SetModes modes, int S, int h,
                                                    int w, int kh, int kw, int akh, int akw, float thresh,
                                                    float* __restrict__ pooled, uint8_t* __restrict__ survive,
                                                    int32_t* __restrict__ rowidx, float* __restrict__ ysum,
                                                    int32_t* __restrict__ counts, int32_t* __restrict__ eff_modes,
                                                    int32_t* __restrict__ status, int32_t* __restrict__ plocal)
 {
-    const int set = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int gh = h / kh, gw = w / kw, N = S * gh * gw;
     const float* y = sup_y + (size_t)set * S * h * w;
     __shared__ int s_warp[8];
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_pool_mask(const float* __restrict__ sup
 // ------------------------------------------------------------------------------------
 // K1b: one CTA per (window, set): pooled feature vector of a surviving window, L2-normalised
 // (clamp 1e-4), written at its compacted row.  Threads run along C (coalesced when the
-// tensor is channels-last).  grid = (N, nsets), block = 256, C <= 256*16.
+// tensor is channels-last).  CTAs 0..N-1 of each set's row in k_proto_stage2, block = 256, C <= 256*16.
 // ------------------------------------------------------------------------------------
 constexpr int kMaxCPerThread = 16;
 
@@ -136,12 +136,18 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_red)
     return t;
 }
 
-__global__ void __launch_bounds__(256) k_pool_feat(const float* __restrict__ sup_x, int64_t xs_s, int64_t xs_c,
-                                                   int64_t xs_y, int64_t xs_x, const int32_t* __restrict__ rowidx,
-                                                   int S, int C, int h, int w, int kh, int kw, int cap_rows,
-                                                   float* __restrict__ protos)
+// Feature tiles are staged with the TMA engine when the tensor is channels-last (the layout DINOv2 hands over): the
+// kh*kw pixels of a window are kh*kw contiguous C-float rows, fetched as kh*kw bulk copies (cp.async.bulk, completion
+// counted in bytes on an mbarrier) by one thread while the CTA's other warps only wait; strided layouts and windows
+// that do not fit kStageBytes are read with plain coalesced loads.
+constexpr int kStageBytes = 40 * 1024;
+
+__device__ __forceinline__ void pool_feat_body(int n, int set, const float* __restrict__ sup_x, int64_t xs_s, int64_t xs_c,
+                                               int64_t xs_y, int64_t xs_x, const int32_t* __restrict__ rowidx,
+                                               int S, int C, int h, int w, int kh, int kw, int cap_rows,
+                                               float* __restrict__ protos, float* s_stage, uint64_t* s_bar)
 {
-    const int n = blockIdx.x, set = blockIdx.y, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int gh = h / kh, gw = w / kw, N = S * gh * gw;
     const int row = rowidx[(size_t)set * N + n];
     if (row < 0) return;
@@ -149,6 +155,36 @@ __global__ void __launch_bounds__(256) k_pool_feat(const float* __restrict__ sup
     const int s = n / (gh * gw), r = n % (gh * gw), gy = r / gw, gx = r % gw;
     const float* base = sup_x + s * xs_s + (int64_t)(gy * kh) * xs_y + (int64_t)(gx * kw) * xs_x;
     const float div = (float)(kh * kw);
+    const bool staged = xs_c == 1 && (C & 3) == 0 && (size_t)kh * kw * C * sizeof(float) <= (size_t)kStageBytes &&
+                        ((reinterpret_cast<uintptr_t>(sup_x) | (uintptr_t)(xs_s * 4) | (uintptr_t)(xs_y * 4) |
+                          (uintptr_t)(xs_x * 4)) & 15) == 0;
+    if (staged) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                         "r"((uint32_t)(kh * kw * C * sizeof(float))) : "memory");
+            for (int dy = 0; dy < kh; ++dy)
+                for (int dx = 0; dx < kw; ++dx)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     (uint32_t)__cvta_generic_to_shared(s_stage + (size_t)(dy * kw + dx) * C)),
+                                 "l"(base + dy * xs_y + dx * xs_x), "r"((uint32_t)(C * sizeof(float))), "r"(bar)
+                                 : "memory");
+        }
+        __syncthreads();                     // the barrier is initialised before anyone polls it
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "WAIT_STAGE:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t"
+            "@P1 bra DONE_STAGE;\n\t"
+            "bra WAIT_STAGE;\n\t"
+            "DONE_STAGE:\n\t"
+            "}" ::"r"(bar)
+            : "memory");
+    }
     float v[kMaxCPerThread];
     float ss = 0.0f;
 #pragma unroll
@@ -157,8 +193,12 @@ __global__ void __launch_bounds__(256) k_pool_feat(const float* __restrict__ sup
         v[j] = 0.0f;
         if (c < C) {
             float acc = 0.0f;
-            for (int dy = 0; dy < kh; ++dy)
-                for (int dx = 0; dx < kw; ++dx) acc = __fadd_rn(acc, __ldg(base + c * xs_c + dy * xs_y + dx * xs_x));
+            if (staged) {
+                for (int k = 0; k < kh * kw; ++k) acc = __fadd_rn(acc, s_stage[(size_t)k * C + c]);
+            } else {
+                for (int dy = 0; dy < kh; ++dy)
+                    for (int dx = 0; dx < kw; ++dx) acc = __fadd_rn(acc, __ldg(base + c * xs_c + dy * xs_y + dx * xs_x));
+            }
             v[j] = __fdiv_rn(acc, div);
             ss += v[j] * v[j];
         }
@@ -175,16 +215,17 @@ __global__ void __launch_bounds__(256) k_pool_feat(const float* __restrict__ sup
 
 // ------------------------------------------------------------------------------------
 // K1c/K1d: global masked-average prototype  sum(x*y) / (sum(y) + 1e-5)  (alpmodule.py:99-100,
-// 155-156), deterministic two-stage reduction: partial sums per feature row, then a fixed
-// order combine + safe_norm.  grid K1c = (h, S, nsets); grid K1d = (S, nsets).
+// 155-156), deterministic two-stage reduction: partial sums per feature row (CTAs 1..h*S of each set's row in
+// k_proto_stage1), then a fixed order combine + safe_norm (CTAs N..N+S-1 of each set's row in k_proto_stage2).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_global_partial(const float* __restrict__ sup_x, int64_t xs_s, int64_t xs_c,
-                                                        int64_t xs_y, int64_t xs_x, const float* __restrict__ sup_y,
-                                                        const int32_t* __restrict__ eff_modes, SetModes modes, int S,
-                                                        int C, int h, int w, float* __restrict__ partial)
+__device__ __forceinline__ void global_partial_body(int yy, int s, int set, const float* __restrict__ sup_x, int64_t xs_s,
+                                                    int64_t xs_c, int64_t xs_y, int64_t xs_x,
+                                                    const float* __restrict__ sup_y, const SetModes& modes, int S,
+                                                    int C, int h, int w, float* __restrict__ partial)
 {
-    const int yy = blockIdx.x, s = blockIdx.y, set = blockIdx.z, tid = threadIdx.x;
-    if (eff_modes[set] == PSAM_MODE_GRIDCONV) return;
+    const int tid = threadIdx.x;
+    // runs in the same launch as the AUTO_FG decision, so only sets that are 'gridconv' by request are skipped
+    if (modes.m[set] == PSAM_MODE_GRIDCONV) return;
     if (modes.shot[set] >= 0 && s != modes.shot[set]) return;
     const float* m = sup_y + (((size_t)set * S + s) * h + yy) * w;
     const float* base = sup_x + s * xs_s + (int64_t)yy * xs_y;
@@ -199,13 +240,13 @@ __global__ void __launch_bounds__(256) k_global_partial(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) k_global_final(const float* __restrict__ partial,
-                                                      const float* __restrict__ ysum,
-                                                      const int32_t* __restrict__ eff_modes,
-                                                      const int32_t* __restrict__ plocal, SetModes modes, int S, int C,
-                                                      int h, int cap_rows, float* __restrict__ protos)
+__device__ __forceinline__ void global_final_body(int s, int set, const float* __restrict__ partial,
+                                                  const float* __restrict__ ysum,
+                                                  const int32_t* __restrict__ eff_modes,
+                                                  const int32_t* __restrict__ plocal, const SetModes& modes, int S, int C,
+                                                  int h, int cap_rows, float* __restrict__ protos)
 {
-    const int s = blockIdx.x, set = blockIdx.y, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     if (eff_modes[set] == PSAM_MODE_GRIDCONV) return;
     const int sel = modes.shot[set];
     if (sel >= 0 && s != sel) return;
@@ -235,6 +276,48 @@ __global__ void __launch_bounds__(256) k_global_final(const float* __restrict__ 
         int c = tid + j * 256;
         if (c < C) dst[c] = v[j] / nrm;
     }
+}
+
+// ------------------------------------------------------------------------------------
+// The two launches of kernel 1.  get_prototypes (alpmodule.py:108-158) is one logical pass with one true dependency:
+// a window's output row (its rank among the survivors) and the AUTO_FG decision need the whole mask first.
+//   stage 1  grid (1 + h*S, nsets): CTA 0 of a set = the mask pass (K1a), the others = per-row partial sums of the
+//            global prototype (K1c), which do not depend on it;
+//   stage 2  grid (N + S, nsets): CTAs < N = surviving windows (K1b), the others = the global rows (K1d).
+// ------------------------------------------------------------------------------------
+struct ProtoArgs {
+    const float* sup_x;
+    int64_t xs_s, xs_c, xs_y, xs_x;
+    const float* sup_y;
+    int S, C, h, w, kh, kw, akh, akw, cap_rows;
+    float thresh;
+    float *pooled, *ysum, *partial, *protos;
+    uint8_t* survive;
+    int32_t *rowidx, *counts, *eff_modes, *status, *plocal;
+};
+
+__global__ void __launch_bounds__(256) k_proto_stage1(ProtoArgs a, SetModes modes)
+{
+    const int set = blockIdx.y;
+    if (blockIdx.x == 0)
+        pool_mask_body(set, a.sup_y, modes, a.S, a.h, a.w, a.kh, a.kw, a.akh, a.akw, a.thresh, a.pooled, a.survive, a.rowidx,
+                       a.ysum, a.counts, a.eff_modes, a.status, a.plocal);
+    else
+        global_partial_body((blockIdx.x - 1) % a.h, (blockIdx.x - 1) / a.h, set, a.sup_x, a.xs_s, a.xs_c, a.xs_y, a.xs_x,
+                            a.sup_y, modes, a.S, a.C, a.h, a.w, a.partial);
+}
+
+__global__ void __launch_bounds__(256) k_proto_stage2(ProtoArgs a, SetModes modes, int N)
+{
+    extern __shared__ __align__(16) float s_stage[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int set = blockIdx.y;
+    if ((int)blockIdx.x < N)
+        pool_feat_body(blockIdx.x, set, a.sup_x, a.xs_s, a.xs_c, a.xs_y, a.xs_x, a.rowidx, a.S, a.C, a.h, a.w, a.kh, a.kw,
+                       a.cap_rows, a.protos, s_stage, &s_bar);
+    else
+        global_final_body(blockIdx.x - N, set, a.partial, a.ysum, a.eff_modes, a.plocal, modes, a.S, a.C, a.h, a.cap_rows,
+                          a.protos);
 }
 
 // ------------------------------------------------------------------------------------
@@ -402,6 +485,7 @@ extern "C" int psam_tokens_to_features(const float* tokens, int B, int h, int w,
     PSAM_CHECK_ARG(B >= 1 && B <= 65535 && h >= 1 && w >= 1 && C >= 1 && oh >= h && ow >= w && oh <= 65535,
                    "psam_tokens_to_features: bad shape (upsampling only)");
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_tokens_bilinear);
     k_tokens_bilinear<<<dim3(ow, oh, B), 256, 0, stream>>>(tokens, h, w, C, oh, ow, out);
     PSAM_CHECK_LAUNCH("k_tokens_bilinear");
     return PSAM_OK;
@@ -415,6 +499,7 @@ extern "C" int psam_combine_shots(const float* scores, int Q, int L, int S, int 
     const size_t total = (size_t)Q * L * HW;
     const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_combine_shots);
     k_combine_shots<<<grid, 256, 0, stream>>>(scores, Q, L, S, HW, logits);
     PSAM_CHECK_LAUNCH("k_combine_shots");
     return PSAM_OK;
@@ -428,6 +513,7 @@ extern "C" int psam_mask_nearest(const float* src, int n, int H, int W, int h, i
     const size_t total = (size_t)n * h * w;
     const int grid = (int)((total + 255) / 256 < 65535 ? (total + 255) / 256 : 65535);
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_mask_nearest);
     k_mask_nearest<<<grid, 256, 0, stream>>>(src, n, H, W, h, w, dst);
     PSAM_CHECK_LAUNCH("k_mask_nearest");
     return PSAM_OK;
@@ -511,24 +597,22 @@ static int alp_prototypes_impl(const float* sup_x, const int64_t* xs, const floa
     int32_t* plocal = cv.take<int32_t>(nsets);
     float* partial = cv.take<float>((size_t)nsets * S * h * C);
 
+    ProtoArgs a;
+    a.sup_x = sup_x; a.xs_s = xs[0]; a.xs_c = xs[1]; a.xs_y = xs[2]; a.xs_x = xs[3]; a.sup_y = sup_y;
+    a.S = S; a.C = C; a.h = h; a.w = w; a.kh = kh; a.kw = kw; a.akh = auto_kh; a.akw = auto_kw; a.cap_rows = cap_rows;
+    a.thresh = thresh; a.pooled = pooled; a.ysum = ysum; a.partial = partial; a.protos = protos; a.survive = survive;
+    a.rowidx = rowidx; a.counts = counts; a.eff_modes = eff_modes; a.status = status; a.plocal = plocal;
     PSAM_PROF_BEGIN(stream);
-
-    k_pool_mask<<<nsets, 256, 0, stream>>>(sup_y, modes, S, h, w, kh, kw, auto_kh, auto_kw, thresh, pooled, survive,
-                                           rowidx, ysum, counts, eff_modes, status, plocal);
-    PSAM_CHECK_LAUNCH("k_pool_mask");
-    if (N > 0) {
-        PSAM_PROF_BEGIN(stream);
-        k_pool_feat<<<dim3(N, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], rowidx, S, C, h, w, kh, kw,
-                                                        cap_rows, protos);
-        PSAM_CHECK_LAUNCH("k_pool_feat");
-    }
+    PSAM_MAX_CARVEOUT(k_proto_stage1);
+    k_proto_stage1<<<dim3(1 + h * S, nsets), 256, 0, stream>>>(a, modes);
+    PSAM_CHECK_LAUNCH("k_proto_stage1");
+    // feature tiles staged through shared memory by the TMA engine when they fit (see pool_feat_body)
+    const size_t tile = (size_t)kh * kw * C * sizeof(float);
+    const size_t smem = tile <= (size_t)kStageBytes ? tile : 0;
     PSAM_PROF_BEGIN(stream);
-    k_global_partial<<<dim3(h, S, nsets), 256, 0, stream>>>(sup_x, xs[0], xs[1], xs[2], xs[3], sup_y, eff_modes, modes,
-                                                            S, C, h, w, partial);
-    PSAM_CHECK_LAUNCH("k_global_partial");
-    PSAM_PROF_BEGIN(stream);
-    k_global_final<<<dim3(S, nsets), 256, 0, stream>>>(partial, ysum, eff_modes, plocal, modes, S, C, h, cap_rows, protos);
-    PSAM_CHECK_LAUNCH("k_global_final");
+    PSAM_MAX_CARVEOUT(k_proto_stage2);
+    k_proto_stage2<<<dim3(N + S, nsets), 256, smem, stream>>>(a, modes, N);
+    PSAM_CHECK_LAUNCH("k_proto_stage2");
     return PSAM_OK;
 }
 
@@ -546,6 +630,7 @@ extern "C" int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, i
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_proto_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     PSAM_PROF_BEGIN(stream);
+    PSAM_MAX_CARVEOUT(k_proto_grid);
     k_proto_grid<<<1, 256, smem, stream>>>(pooled, S, gh, gw, vw, thresh, mode, out, nullptr);
     PSAM_CHECK_LAUNCH("k_proto_grid");
     return PSAM_OK;

@@ -111,7 +111,7 @@ class CoarseVolumeEngine:
     def __init__(self, feature_hw: Sequence[int], img_size: int, out_size: int = 1024, val_wsize: int = 2,
                  proto_grid_size: int = 8, use_cca: bool = False, point_mode: str = "both",
                  max_cc: int = ops.DEFAULT_MAX_CC, max_runs: int = ops.DEFAULT_MAX_RUNS, fg_mode: str = "auto_fg",
-                 match_algo: int = 0, group=None):
+                 match_algo: int = 0, group=None, variant: str = "protosam"):
         self.h, self.w = int(feature_hw[0]), int(feature_hw[1])
         self.img_size, self.out_size = int(img_size), int(out_size)
         self.val_wsize = int(val_wsize)
@@ -120,6 +120,12 @@ class CoarseVolumeEngine:
         self.use_cca, self.point_mode = bool(use_cca), point_mode
         self.max_cc, self.max_runs = int(max_cc), int(max_runs)
         self.fg_mode, self.match_algo, self.group = fg_mode, match_algo, group
+        # 'protosam': confidences from softmax(logits) (models/ProtoSAM.py:599-608); 'medsam': ProtoMedSAM hands cca()
+        # probabilities, which it soft-maxes again (models/ProtoMedSAM.py:178-187) -- only boxes are used downstream
+        if variant not in ("protosam", "medsam"):
+            raise ValueError("variant must be 'protosam' or 'medsam'")
+        self.variant = variant
+        self.prob_mode = "softmax_twice" if variant == "medsam" else "softmax"
         self.protos: Optional[dict] = None
         self.n_labels, self.n_shots = 0, 1
         self._ws = None
@@ -189,7 +195,8 @@ class CoarseVolumeEngine:
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=logits.device)
         return ops.coarse_to_prompts(logits, self.img_size, self.out_size, self.use_cca, self.max_cc,
-                                     self.max_runs, workspace=self._ws, n_alloc=n_alloc, return_packed=return_packed)
+                                     self.max_runs, workspace=self._ws, n_alloc=n_alloc, return_packed=return_packed,
+                                     prob_mode=self.prob_mode)
 
     def run(self, qry_feats: torch.Tensor):
         """-> (hdr, recs) on the device; image index = q*L + l."""

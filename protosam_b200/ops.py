@@ -186,9 +186,14 @@ def alp_match(qry, protos, want_assign=True, want_sims=False, algo=0):
 
 # ------------------------------------------------------------------ kernel 3
 
-def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False, fg_only=False, want_wstat=False):
-    """logits [n,2,h,w] -> (p_fg [n,out,out] | None, maskbits [n,out,out//32] int32, probs2 | None
-    [, wstat int64 [n,out,out//32]]).  fg_only: the engine's variant (p_fg valid at foreground pixels only)."""
+PROB_MODES = {"softmax": _lib.PROB_SOFTMAX, "softmax_twice": _lib.PROB_SOFTMAX_TWICE}
+
+
+def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False, fg_only=False, want_wstat=False,
+                     prob_mode="softmax"):
+    """logits [n,2,h,w] -> (p_fg [n,out,out] | None, maskbits [n,out,ceil(out/32)] int32, probs2 | None
+    [, wstat int64 [n,out,ceil(out/32)]]).  fg_only: the engine's variant (p_fg written only where kernel 3b reads it).
+    prob_mode 'softmax_twice': p_fg / wstat carry softmax(softmax(logits))[1], ProtoMedSAM's confidence map."""
     L = _lib.load()
     _need_cuda(logits)
     logits = logits.contiguous()
@@ -204,7 +209,7 @@ def upsample_softmax(logits, mid, out=1024, want_p_fg=True, want_probs2=False, f
         p_fg.zero_()
     ws = _ws(L.psam_upsample_workspace(n, int(out)), dev)
     rc = L.psam_upsample_softmax(_ptr(logits), n, h, w, int(mid), int(out), _ptr(p_fg), _ptr(bits), _ptr(probs2),
-                                 _ptr(wstat), int(bool(fg_only)), _ptr(ws), ws.numel(), _stream())
+                                 _ptr(wstat), int(bool(fg_only)), PROB_MODES[prob_mode], _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "psam_upsample_softmax")
     if want_wstat:
         return p_fg, bits, probs2, wstat
@@ -244,7 +249,7 @@ def split_records(buf, max_cc):
 
 
 def coarse_to_prompts(logits, mid, out=1024, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DEFAULT_MAX_RUNS,
-                      workspace=None, n_alloc=None, return_packed=False):
+                      workspace=None, n_alloc=None, return_packed=False, prob_mode="softmax"):
     """logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on device, one call.  n_alloc >= n sizes
     the (zero-padded) output buffer, e.g. to the largest shard of a multi-GPU run."""
     L = _lib.load()
@@ -256,12 +261,61 @@ def coarse_to_prompts(logits, mid, out=1024, use_cca=False, max_cc=DEFAULT_MAX_C
     buf, hdr, recs = records_alloc(max(n_alloc or n, n), max_cc, dev)
     need = L.psam_coarse_to_prompts_workspace(n, out, max_runs, max_cc)
     ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
-    rc = L.psam_coarse_to_prompts(_ptr(logits), n, h, w, int(mid), int(out), int(bool(use_cca)), max_cc, max_runs,
-                                  _ptr(hdr), _ptr(recs), _ptr(ws), ws.numel(), _stream())
+    rc = L.psam_coarse_to_prompts(_ptr(logits), n, h, w, int(mid), int(out), int(bool(use_cca)), PROB_MODES[prob_mode],
+                                  max_cc, max_runs, _ptr(hdr), _ptr(recs), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "psam_coarse_to_prompts")
     if return_packed:
         return hdr[:n], recs[:n], buf
     return hdr[:n], recs[:n]
+
+
+NEG_DTYPE = np.dtype([("pt", "<i8", 2), ("p", "<f4"), ("has", "<i4"), ("n", "<i4"), ("reserved", "<i4")])
+assert NEG_DTYPE.itemsize == 32
+
+
+def neg_points(labels, p_bg, hdr, recs, use_cca=False, ring_width=10, thresh=0.95, host_aliasing=False):
+    """Negative-point candidates (ProtoSAM.get_sam_input_points with get_neg_points=True, models/ProtoSAM.py:361-434):
+    labels int32 [n,out,out] (psam_components), p_bg [n,out,out] view of the background probabilities (its image
+    stride may be larger: channel 0 of probs2) -> uint8 [n, max_cc + 1, 32] records (NEG_DTYPE): [i, r] the ring point
+    of component r, [i, max_cc] the image's global point."""
+    L = _lib.load()
+    _need_cuda(p_bg)
+    n, out, _ = labels.shape
+    max_cc = recs.shape[1]
+    assert p_bg.stride(2) == 1 and p_bg.stride(1) == out and labels.is_contiguous()
+    neg = torch.empty((n, max_cc + 1, NEG_DTYPE.itemsize), dtype=torch.uint8, device=labels.device)
+    rc = L.psam_neg_points(_ptr(labels), _ptr(p_bg), p_bg.stride(0), _ptr(hdr.contiguous()), _ptr(recs.contiguous()), n, out,
+                           max_cc, int(bool(use_cca)), int(ring_width), float(thresh), int(bool(host_aliasing)), _ptr(neg),
+                           _stream())
+    _lib.check(rc, "psam_neg_points")
+    return neg
+
+
+def mask_prompts(labels, hdr, recs, use_cca=False, size=256, capacity=None):
+    """Mask prompts (models/ProtoSAM.py:452-476): -> (masks uint8 [capacity,size,size] with 10 / 248, offsets int32 [n+1]);
+    component r of image i is masks[offsets[i] + r]."""
+    L = _lib.load()
+    n, out, _ = labels.shape
+    max_cc = recs.shape[1]
+    capacity = int(capacity) if capacity is not None else n * max_cc
+    masks = torch.empty((capacity, size, size), dtype=torch.uint8, device=labels.device)
+    offsets = torch.zeros(n + 1, dtype=torch.int32, device=labels.device)
+    rc = L.psam_mask_prompts(_ptr(labels), _ptr(hdr.contiguous()), _ptr(recs.contiguous()), n, out, max_cc,
+                             int(bool(use_cca)), int(size), capacity, _ptr(masks), _ptr(offsets), _stream())
+    _lib.check(rc, "psam_mask_prompts")
+    return masks, offsets
+
+
+def confidence(p_fg):
+    """get_confidence_from_logits (util/utils.py:429-434) from p_fg [n, ...]: float64 [n] on the device."""
+    L = _lib.load()
+    _need_cuda(p_fg)
+    p_fg = p_fg.contiguous()
+    n = p_fg.shape[0]
+    conf = torch.empty(n, dtype=torch.float64, device=p_fg.device)
+    rc = L.psam_confidence(_ptr(p_fg), n, p_fg.numel() // n, _ptr(conf), _stream())
+    _lib.check(rc, "psam_confidence")
+    return conf
 
 
 POINT_MODE_IDS = {"conf": 0, "centroid": 1, "both": 2}

@@ -126,6 +126,30 @@ def test_engine_match_vs_reference_golden(cfg_name):
                     np.testing.assert_allclose(logits[q * L + l, si % 2], ref, atol=MAP_TOL, rtol=0)
 
 
+@pytest.mark.parametrize("key", ["cfg3_synapse_ct", "cfg4_polyp_1024", "cfg5_ws3", "cfg5_ws6", "cfg5_ws7"])
+def test_engine_match_vs_reference_golden_remaining_configs(key):
+    """BASELINE configs 3, 4 and the ws = 3, 6, 7 points of config 5 (C = 1024) against maps and survival masks the
+    unmodified reference produced (tests/golden/alp_configs2.npz)."""
+    g = _load("alp_configs2.npz")
+    seed, nq, L, ws = [int(v) for v in g[f"{key}/meta"]]
+    cfg = synth.CONFIGS[key if key in synth.CONFIGS else "cfg5_stress_vitl"]
+    vol = synth.make_volume(seed, Q=nq, L=L, C=cfg["C"], h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    kinds = sorted({n.split("/")[3] for n in g["names"] if n.startswith(key + "/")})
+    for fg_mode, kind in (("gridconv+", "fg"), ("mask", "fgmask")):
+        if kind not in kinds:
+            continue
+        eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=ws, fg_mode=fg_mode)
+        pr = eng.set_support(_t(vol.sup), _t(vol.fg))
+        logits = eng.match(_t(vol.qry)).cpu().numpy()               # [Q*L,2,h,w]
+        N = pr["N"]
+        for l in range(L):
+            for name, si in (("bg", 2 * l), (kind, 2 * l + 1)):
+                if name != "fgmask":
+                    assert np.array_equal(pr["survive"][si, :N].cpu().numpy().astype(bool), g[f"{key}/l{l}/q0/{name}/survive"])
+                ref = g[f"{key}/l{l}/q0/{name}/pred_grid"][0, 0]
+                np.testing.assert_allclose(logits[l, si % 2], ref, atol=MAP_TOL, rtol=0)
+
+
 def test_engine_auto_fg_mode_matches_caller_rule():
     """grid_proto_fewshot.py:254-256: 'gridconv+' iff some kernel_size window is >= 0.95 foreground."""
     h = w = 32
@@ -637,7 +661,7 @@ def test_graphed_volume_step_replays_equal_eager_run():
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         gs = GraphedVolumeStep(eng, sup, fg, qry)
-        assert gs.n_kernels == 4 + 3 + 3            # kernel 1 (4 launches), pack x2 + GEMM, classify + exact + components
+        assert gs.n_kernels == 2 + 3 + 3            # kernel 1 (2 launches), pack x2 + GEMM, classify + blocks + components
         h1, r1 = gs.launch()
         h1, r1 = h1.clone(), r1.clone()
         sup.copy_(_t(vol2.sup)); fg.copy_(_t(vol2.fg)); qry.copy_(_t(vol2.qry))

@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25
+for v in "3 3"; do set -- $v
+  PSAM_TC_STAGES=$1 PSAM_BW_CTAS=$2 timeout 300 python bench.py --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/r2e_bench_s$1_c$2.json 2> gpurun_out/r2e_bench_s$1_c$2.err
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/r2e_bench_s$1_c$2.json"))
+print("stages $1 ctas $2", d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["kernels_ms_per_step"])
+PY
+done
