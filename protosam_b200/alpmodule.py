@@ -11,7 +11,10 @@ Differences that are deliberate:
     stay on the reference module);
   * ``proto_grid`` (viz-only 4th output) is a CUDA tensor; the reference builds it on the CPU;
   * an invalid ``mode`` raises ``ValueError`` up front (the reference trips an
-    ``UnboundLocalError`` in get_prototypes before reaching its own ValueError at :93-94).
+    ``UnboundLocalError`` in get_prototypes before reaching its own ValueError at :93-94);
+  * ``forward`` never synchronises the host: the reference's error for an empty 'gridconv' set is raised by
+    ``raise_if_empty()`` (or inside forward when ``check_empty = True``), see ``__init__``.  ``vis_sim=True`` (debug
+    visualisation) does read the prototype count back to slice ``raw_local_sims``.
 """
 from __future__ import annotations
 
@@ -47,10 +50,20 @@ class MultiProtoAsConv(nn.Module):
                                      nn.ReLU(inplace=True), nn.Conv2d(128, 1, 1))
             self.fg_mask_projection = proj()
             self.bg_mask_projection = proj()
-        # reference behaviour on an empty 'gridconv' set: print + RuntimeError from F.conv2d.
-        # Checking costs one 4-byte device->host read per call; the batched engine never does it.
-        self.check_empty = True
+        # An empty 'gridconv' set: the reference prints and raises (RuntimeError from F.conv2d, :193-194 / :68).  Knowing
+        # that inside forward() costs a device->host read per call, so by default forward() does NOT synchronise: the
+        # scores of such a call are NaN, the set's status word stays on the device in `last_status`, and
+        # raise_if_empty() (one 4-byte read, whenever the caller likes -- e.g. once per volume) turns it into the
+        # reference's error.  check_empty = True restores the reference's raise-inside-forward behaviour.
+        self.check_empty = False
+        self.last_status = None
         self.match_algo = 0
+
+    def raise_if_empty(self):
+        """The reference's error for the LAST forward() call, on demand (see __init__)."""
+        if self.last_status is not None and int(self.last_status[0].item()) & _lib.SET_EMPTY:
+            print("failed to find prototypes")      # :193-194, then F.conv2d raises on a [0,C,1,1] weight
+            raise RuntimeError("no prototypes survived the threshold: conv2d with a weight of size [0, C, 1, 1]")
 
     def forward(self, qry, sup_x, sup_y, mode, thresh, isval=False, val_wsize=None, vis_sim=False,
                 get_prototypes=False, **kwargs):
@@ -78,10 +91,9 @@ class MultiProtoAsConv(nn.Module):
         ops._need_cuda(qry, sup_x, sup_y)
 
         protos = ops.alp_prototypes(sup_x, sup_y.reshape(1, S, h, w), [mode], ksize, thresh)
+        self.last_status = protos["status"]
         if mode == "gridconv" and self.check_empty:
-            if int(protos["status"][0].item()) & _lib.SET_EMPTY:
-                print("failed to find prototypes")  # :193-194, then F.conv2d raises on a [0,C,1,1] weight
-                raise RuntimeError("no prototypes survived the threshold: weight of size [0, %d, 1, 1]" % C)
+            self.raise_if_empty()
 
         Q = qry.shape[0]
         q = qry.permute(0, 2, 3, 1)                 # channels-last view; a no-op for DINOv2 tokens

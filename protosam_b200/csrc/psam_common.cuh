@@ -2,12 +2,23 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
 #include "../../include/psam_b200.h"
 
 namespace psam {
+
+// ---- tracing: every entry point of the C ABI that enqueues work is an NVTX range (header-only NVTX3: a no-op unless
+// a tool such as nsys / ncu --nvtx is attached), so timelines and `ncu --nvtx-include` can be cut per stage ----
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define PSAM_TRACE(name) psam::NvtxRange nvtx_range__(name)
 
 // ---- host-side error plumbing (thread-local message, see psam_last_error) ----
 void set_error(const char* fmt, ...);

@@ -716,6 +716,7 @@ extern "C" size_t psam_packed_bytes(int n_alloc, int capacity)
 extern "C" int psam_compact_records(const psam_image_hdr* hdr, const psam_prompt_rec* recs, int n_img, int n_alloc, int max_cc,
                                     int capacity, void* packed, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_compact_records");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(hdr && recs && packed, "psam_compact_records: null pointer");
     PSAM_CHECK_ARG(n_img >= 1 && n_alloc >= n_img && max_cc >= 1 && capacity >= 1, "psam_compact_records: bad shape");
@@ -757,6 +758,7 @@ extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, cons
                                int max_cc, int max_runs, psam_image_hdr* hdr, psam_prompt_rec* recs,
                                int32_t* labels_out, void* workspace, size_t workspace_bytes, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_components");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(maskbits && p_fg && hdr && recs && workspace, "psam_components: null pointer");
     PSAM_CHECK_ARG(n_img >= 1, "psam_components: n_img %d", n_img);
@@ -818,6 +820,7 @@ extern "C" int psam_coarse_to_prompts(const float* logits, int n_img, int h, int
                                       int prob_mode, int max_cc, int max_runs, psam_image_hdr* hdr, psam_prompt_rec* recs,
                                       void* workspace, size_t workspace_bytes, psam_stream_t stream)
 {
+    PSAM_TRACE("psam_coarse_to_prompts");
     PSAM_CHECK_ARG(workspace, "psam_coarse_to_prompts: null workspace");
     if (workspace_bytes < psam_coarse_to_prompts_workspace(n_img, out, max_runs, max_cc)) {
         set_error("psam_coarse_to_prompts: workspace too small");
@@ -840,6 +843,7 @@ extern "C" int psam_records_to_sam(const psam_image_hdr* hdr, const psam_prompt_
                                    int point_mode, int old_h, int old_w, int target_length, float* points,
                                    int32_t* labels, float* boxes, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_records_to_sam");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(hdr && recs && points && labels && boxes, "psam_records_to_sam: null pointer");
     PSAM_CHECK_ARG(n_img >= 1 && max_cc >= 1 && point_mode >= 0 && point_mode <= 2 && old_h >= 1 && old_w >= 1 &&

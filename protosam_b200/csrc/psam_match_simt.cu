@@ -215,6 +215,7 @@ extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t ro
                               int nsets, float* scores, float* assign, float* sims, int32_t* status, void* workspace,
                               size_t workspace_bytes, int algo, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_alp_match");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(qry && protos && counts && eff_modes && scores && status, "psam_alp_match: null pointer");
     PSAM_CHECK_ARG(Q >= 1 && Q <= 65535 && HW >= 1 && C >= 1 && nsets >= 1 && nsets <= 65535 && cap_rows >= 1,

@@ -480,6 +480,7 @@ using namespace psam;
 extern "C" int psam_tokens_to_features(const float* tokens, int B, int h, int w, int C, int oh, int ow, float* out,
                                        psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_tokens_to_features");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(tokens && out, "psam_tokens_to_features: null pointer");
     PSAM_CHECK_ARG(B >= 1 && B <= 65535 && h >= 1 && w >= 1 && C >= 1 && oh >= h && ow >= w && oh <= 65535,
@@ -493,6 +494,7 @@ extern "C" int psam_tokens_to_features(const float* tokens, int B, int h, int w,
 
 extern "C" int psam_combine_shots(const float* scores, int Q, int L, int S, int HW, float* logits, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_combine_shots");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(scores && logits, "psam_combine_shots: null pointer");
     PSAM_CHECK_ARG(Q >= 1 && L >= 1 && S >= 1 && HW >= 1, "psam_combine_shots: bad shape");
@@ -507,6 +509,7 @@ extern "C" int psam_combine_shots(const float* scores, int Q, int L, int S, int 
 
 extern "C" int psam_mask_nearest(const float* src, int n, int H, int W, int h, int w, float* dst, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_mask_nearest");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(src && dst, "psam_mask_nearest: null pointer");
     PSAM_CHECK_ARG(n >= 1 && H >= 1 && W >= 1 && h >= 1 && w >= 1, "psam_mask_nearest: bad shape");
@@ -543,6 +546,7 @@ extern "C" int psam_alp_prototypes(const float* sup_x, const int64_t* xs, const 
                                    int32_t* eff_modes, int32_t* status, uint8_t* survive, float* pooled,
                                    void* workspace, size_t workspace_bytes, psam_stream_t stream)
 {
+    PSAM_TRACE("psam_alp_prototypes");
     return alp_prototypes_impl(sup_x, xs, sup_y, nsets, set_modes, nullptr, S, C, h, w, kh, kw, auto_kh, auto_kw, thresh,
                                protos, counts, eff_modes, status, survive, pooled, workspace, workspace_bytes, stream);
 }
@@ -553,6 +557,7 @@ extern "C" int psam_alp_prototypes_shots(const float* sup_x, const int64_t* xs, 
                                          int32_t* counts, int32_t* eff_modes, int32_t* status, uint8_t* survive,
                                          float* pooled, void* workspace, size_t workspace_bytes, psam_stream_t stream)
 {
+    PSAM_TRACE("psam_alp_prototypes_shots");
     PSAM_CHECK_ARG(set_shots, "psam_alp_prototypes_shots: null set_shots");
     return alp_prototypes_impl(sup_x, xs, sup_y, nsets, set_modes, set_shots, S, C, h, w, kh, kw, auto_kh, auto_kw, thresh,
                                protos, counts, eff_modes, status, survive, pooled, workspace, workspace_bytes, stream);
@@ -619,6 +624,7 @@ static int alp_prototypes_impl(const float* sup_x, const int64_t* xs, const floa
 extern "C" int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, int vw, float thresh, int mode,
                                    float* out, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_alp_proto_grid");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(pooled && out, "psam_alp_proto_grid: null pointer");
     PSAM_CHECK_ARG(S >= 1 && gh >= 0 && gw >= 0 && vw >= 1, "psam_alp_proto_grid: bad shape");

@@ -243,6 +243,7 @@ extern "C" int psam_neg_points(const int32_t* labels, const float* p_bg, int64_t
                                const psam_prompt_rec* recs, int n_img, int out, int max_cc, int use_cca, int ring_width,
                                float thresh, int host_aliasing, psam_neg_point* neg, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_neg_points");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(labels && p_bg && hdr && recs && neg, "psam_neg_points: null pointer");
     PSAM_CHECK_ARG(n_img >= 1 && n_img <= 65535 && out >= 1 && out <= NT && max_cc >= 1, "psam_neg_points: bad shape (out <= %d)", NT);
@@ -264,6 +265,7 @@ extern "C" int psam_mask_prompts(const int32_t* labels, const psam_image_hdr* hd
                                  int max_cc, int use_cca, int size, int capacity, uint8_t* masks, int32_t* offsets,
                                  psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_mask_prompts");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(labels && hdr && recs && masks && offsets, "psam_mask_prompts: null pointer");
     PSAM_CHECK_ARG(n_img >= 1 && n_img <= 65535 && out >= 1 && max_cc >= 1 && size >= 1 && capacity >= 1, "psam_mask_prompts: bad shape");
@@ -277,6 +279,7 @@ extern "C" int psam_mask_prompts(const int32_t* labels, const psam_image_hdr* hd
 
 extern "C" int psam_confidence(const float* p_fg, int n_img, int64_t pixels_per_image, double* conf, psam_stream_t stream_)
 {
+    PSAM_TRACE("psam_confidence");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSAM_CHECK_ARG(p_fg && conf, "psam_confidence: null pointer");
     PSAM_CHECK_ARG(n_img >= 1 && pixels_per_image >= 1, "psam_confidence: bad shape");

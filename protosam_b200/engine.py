@@ -19,6 +19,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -53,15 +54,20 @@ def broadcast_prototypes(protos: dict, src: int = 0, group=None) -> dict:
 
 class PendingGather:
     """Handle of an in-flight record gather (NCCL runs it on its own stream, so the next volume's kernels
-    overlap it).  result() waits and returns (hdr_all, recs_all) on dst, (None, None) elsewhere."""
+    overlap it).  result() waits and returns (hdr_all, recs_all) on dst, (None, None) elsewhere.
 
-    def __init__(self, work, bucket, counts, max_cc, keep):
-        self.work, self.bucket, self.counts, self.max_cc, self.keep = work, bucket, counts, max_cc, keep
+    layout = ("dense", max_cc): per-rank buffers are ops.records_alloc images, the result is dense
+             (hdr [n,64], recs [n,max_cc,96]);
+             ("compact", n_alloc, capacity): per-rank buffers are ops.compact_records images, the result is compact
+             (hdr [n,64] with hdr.reserved rebased to the merged record list, recs [total,96])."""
+
+    def __init__(self, work, bucket, counts, layout, keep):
+        self.work, self.bucket, self.counts, self.layout, self.keep = work, bucket, counts, layout, keep
         self._ready = None
 
     @classmethod
     def done(cls, pair):
-        p = cls(None, None, [], 0, None)
+        p = cls(None, None, [], ("dense", 0), None)
         p._ready = pair
         return p
 
@@ -77,23 +83,40 @@ class PendingGather:
         self.wait()
         if self.bucket is None:
             return None, None
-        parts = [ops.split_records(b, self.max_cc) for b in self.bucket]
-        return (torch.cat([h[:c] for (h, _), c in zip(parts, self.counts)], 0),
-                torch.cat([r[:c] for (_, r), c in zip(parts, self.counts)], 0))
+        if self.layout[0] == "dense":
+            parts = [ops.split_records(b, self.layout[1]) for b in self.bucket]
+            return (torch.cat([h[:c] for (h, _), c in zip(parts, self.counts)], 0),
+                    torch.cat([r[:c] for (_, r), c in zip(parts, self.counts)], 0))
+        _, n_alloc, cap = self.layout
+        parts = [ops.split_packed(b, n_alloc, cap) for b in self.bucket]
+        tails = torch.stack([t for _, t, _ in parts]).cpu().numpy()          # one small device->host read
+        T = tails.view(ops.TAIL_DTYPE).reshape(-1)
+        if (T["flags"] & ops._lib.PACKED_OVERFLOW).any():
+            raise RuntimeError("a rank produced more prompt records than the compact buffer holds; raise recs_per_image")
+        hdrs, recs, base = [], [], 0
+        for (h, _, r), c, t in zip(parts, self.counts, T):
+            h = h[:c].clone()
+            h.view(torch.int32)[:, 15] += base                                # hdr.reserved: first record of the image
+            hdrs.append(h)
+            recs.append(r[: int(t["total"])])
+            base += int(t["total"])
+        return torch.cat(hdrs, 0), torch.cat(recs, 0)
 
 
-def gather_packed(buf: torch.Tensor, counts: Sequence[int], max_cc: int, dst: int = 0, group=None,
-                  async_op: bool = False):
-    """ONE gather of the per-rank packed (headers | records) buffers, all sized for max(counts) images."""
+def gather_packed(buf: torch.Tensor, counts: Sequence[int], layout, dst: int = 0, group=None, async_op: bool = False):
+    """ONE gather of the per-rank packed buffers (all of the same size: sized for max(counts) images).  `layout` as in
+    PendingGather; an int is taken as ("dense", max_cc)."""
+    if isinstance(layout, int):
+        layout = ("dense", layout)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     bucket = list(torch.empty((world, buf.numel()), dtype=buf.dtype, device=buf.device).unbind(0)) if rank == dst else None
     work = dist.gather(buf, bucket, dst=dst, group=group, async_op=async_op)
-    pend = PendingGather(work if async_op else None, bucket, list(counts), max_cc, buf)
+    pend = PendingGather(work if async_op else None, bucket, list(counts), layout, buf)
     return pend if async_op else pend.result()
 
 
 def gather_records(hdr: torch.Tensor, recs: torch.Tensor, counts: Sequence[int], dst: int = 0, group=None):
-    """Gather per-rank (hdr [n_r,64], recs [n_r,max_cc,96]) to `dst` in rank order.  `counts` = images
+    """Gather per-rank dense (hdr [n_r,64], recs [n_r,max_cc,96]) to `dst` in rank order.  `counts` = images
     per rank (known from shard_range, no size exchange needed).  Returns (hdr_all, recs_all) on dst,
     (None, None) elsewhere."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -102,7 +125,7 @@ def gather_records(hdr: torch.Tensor, recs: torch.Tensor, counts: Sequence[int],
     buf, h, r = ops.records_alloc(nmax, max_cc, hdr.device)
     h[: hdr.shape[0]] = hdr
     r[: recs.shape[0]] = recs
-    return gather_packed(buf, counts, max_cc, dst=dst, group=group)
+    return gather_packed(buf, counts, ("dense", max_cc), dst=dst, group=group)
 
 
 class CoarseVolumeEngine:
@@ -111,7 +134,8 @@ class CoarseVolumeEngine:
     def __init__(self, feature_hw: Sequence[int], img_size: int, out_size: int = 1024, val_wsize: int = 2,
                  proto_grid_size: int = 8, use_cca: bool = False, point_mode: str = "both",
                  max_cc: int = ops.DEFAULT_MAX_CC, max_runs: int = ops.DEFAULT_MAX_RUNS, fg_mode: str = "auto_fg",
-                 match_algo: int = 0, group=None, variant: str = "protosam"):
+                 match_algo: int = 0, group=None, variant: str = "protosam",
+                 recs_per_image: int = ops.DEFAULT_RECS_PER_IMAGE):
         self.h, self.w = int(feature_hw[0]), int(feature_hw[1])
         self.img_size, self.out_size = int(img_size), int(out_size)
         self.val_wsize = int(val_wsize)
@@ -119,6 +143,7 @@ class CoarseVolumeEngine:
         self.kernel_size = (self.h // proto_grid_size, self.w // proto_grid_size)
         self.use_cca, self.point_mode = bool(use_cca), point_mode
         self.max_cc, self.max_runs = int(max_cc), int(max_runs)
+        self.recs_per_image = int(recs_per_image)      # capacity of the compact record buffers, per image
         self.fg_mode, self.match_algo, self.group = fg_mode, match_algo, group
         # 'protosam': confidences from softmax(logits) (models/ProtoSAM.py:599-608); 'medsam': ProtoMedSAM hands cca()
         # probabilities, which it soft-maxes again (models/ProtoMedSAM.py:178-187) -- only boxes are used downstream
@@ -189,14 +214,16 @@ class CoarseVolumeEngine:
         return scores.view(Q * self.n_labels, 2, h, w)
 
     def prompts_from_logits(self, logits: torch.Tensor, n_alloc=None, return_packed=False):
-        """coarse logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on the device."""
+        """coarse logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on the device; return_packed adds the
+        compact buffer (headers + live records only, sized for n_alloc images) that gathers and host copies move."""
         n = logits.shape[0]
         need = ops._lib.load().psam_coarse_to_prompts_workspace(n, self.out_size, self.max_runs, self.max_cc)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=logits.device)
         return ops.coarse_to_prompts(logits, self.img_size, self.out_size, self.use_cca, self.max_cc,
                                      self.max_runs, workspace=self._ws, n_alloc=n_alloc, return_packed=return_packed,
-                                     prob_mode=self.prob_mode)
+                                     prob_mode=self.prob_mode,
+                                     capacity=max(n_alloc or 0, logits.shape[0]) * self.recs_per_image)
 
     def run(self, qry_feats: torch.Tensor):
         """-> (hdr, recs) on the device; image index = q*L + l."""
@@ -211,14 +238,37 @@ class CoarseVolumeEngine:
             out = self.run(qry_local)
             return PendingGather.done(out) if async_op else out
         _, _, buf = self.prompts_from_logits(self.match(qry_local), n_alloc=max(counts), return_packed=True)
-        return gather_packed(buf, counts, self.max_cc, dst=dst, group=self.group, async_op=async_op)
+        return gather_packed(buf, counts, ("compact", max(counts), max(counts) * self.recs_per_image), dst=dst,
+                             group=self.group, async_op=async_op)
 
-    def decode(self, hdr: torch.Tensor, recs: torch.Tensor) -> List[List[P.SlicePrompts]]:
-        """Device records -> per slice, per label prompt objects (one D2H copy)."""
-        H, R = ops.decode_headers(hdr), ops.decode_records(recs)
+    def decode(self, hdr: torch.Tensor, recs: torch.Tensor, on_empty_set: str = "raise") -> List[List[P.SlicePrompts]]:
+        """Device records -> per slice, per label prompt objects (one D2H copy).  recs is dense [n,max_cc,96] or compact
+        [total,96] (then image i owns recs[hdr.reserved : hdr.reserved + hdr.n_rec]).  on_empty_set: 'raise' (the
+        reference's behaviour, see check_status) or 'ignore' (such labels decode as empty prompts: their scores are NaN)."""
+        if on_empty_set == "raise":
+            self.check_status()
+        H = ops.decode_headers(hdr)
+        if recs.dim() == 3:
+            R = ops.decode_records(recs)
+            per = [R[i] for i in range(len(H))]
+        else:
+            Rc = np.frombuffer(recs.detach().cpu().numpy().tobytes(), dtype=ops.REC_DTYPE)
+            per = [Rc[int(h["reserved"]): int(h["reserved"]) + int(h["n_rec"])] for h in H]
         L = self.n_labels
-        flat = [P.prompts_from_records(H[i], R[i], self.use_cca, self.point_mode) for i in range(len(H))]
+        flat = [P.prompts_from_records(H[i], per[i], self.use_cca, self.point_mode) for i in range(len(H))]
         return [flat[q * L:(q + 1) * L] for q in range(len(flat) // L)]
+
+    def check_status(self):
+        """The reference raises when a 'gridconv' set has no prototype (F.conv2d on a [0,C,1,1] weight,
+        models/alpmodule.py:68); the batched path records it in the device-side status words instead of synchronising
+        per call.  decode() -- the first point where the host reads results anyway -- turns it back into the error."""
+        if self.protos is not None and self.protos.get("status") is not None:
+            st = self.protos["status"].detach().cpu().numpy()
+            bad = np.nonzero(st & ops._lib.SET_EMPTY)[0]
+            if len(bad):
+                print("failed to find prototypes")
+                raise RuntimeError(f"no prototypes survived the threshold in 'gridconv' set(s) {bad.tolist()} "
+                                   "(the reference raises inside F.conv2d)")
 
 
 class GraphedVolumeStep:
@@ -232,7 +282,9 @@ class GraphedVolumeStep:
         gather                     of the packed records (one NCCL call, asynchronous)
 
     `sup_feats`, `fg_masks`, `qry_local` are the buffers the graphs read: refill them in place (or copy new data
-    into them on the same stream) before each `launch()`.
+    into them on the same stream) before each `launch()`.  `self.buf` is the compact record buffer of the last
+    launch (ops.decode_packed / ops.split_packed read it); it lives in graph 2's memory pool, so the next launch()
+    rewrites it -- launch() therefore first makes the stream wait for the previous launch's asynchronous gather.
     """
 
     def __init__(self, eng: CoarseVolumeEngine, sup_feats: torch.Tensor, fg_masks: torch.Tensor,
@@ -262,10 +314,16 @@ class GraphedVolumeStep:
             self.hdr, self.recs, self.buf = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc,
                                                                     return_packed=True)
         self.n_kernels = int(ops._lib.launch_count() - k0)      # library kernels one launch() replays
+        self.n_alloc = n_alloc
+        self.layout = ("compact", n_alloc, n_alloc * eng.recs_per_image)
+        self._pending = None
 
     def launch(self, async_gather: bool = True, gather: bool = True):
         """Enqueue one volume on the current stream.  -> this rank's (hdr, recs) device views when world == 1 or
         gather is False, else a PendingGather (or the gathered pair when async_gather is False)."""
+        if self._pending is not None and isinstance(self._pending, PendingGather):
+            self._pending.wait()         # graph 2 rewrites self.buf: the previous volume's gather must have read it
+            self._pending = None
         if self.g1 is not None:
             self.g1.replay()
         if self.world > 1:
@@ -274,8 +332,9 @@ class GraphedVolumeStep:
         if self.world == 1 or not gather:
             n = self.counts[self.rank]
             return self.hdr[:n], self.recs[:n]
-        return gather_packed(self.buf, self.counts, self.eng.max_cc, dst=self.dst, group=self.eng.group,
-                             async_op=async_gather)
+        out = gather_packed(self.buf, self.counts, self.layout, dst=self.dst, group=self.eng.group, async_op=async_gather)
+        self._pending = out if async_gather else None
+        return out
 
 
 # ---------------------------------------------------------------------------------------------

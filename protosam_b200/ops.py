@@ -248,25 +248,71 @@ def split_records(buf, max_cc):
             buf[n_alloc * HDR_DTYPE.itemsize:].view(n_alloc, max_cc, REC_DTYPE.itemsize))
 
 
+TAIL_DTYPE = np.dtype([("total", "<i4"), ("capacity", "<i4"), ("flags", "<i4"), ("n_img", "<i4"), ("reserved", "<i4", 12)])
+assert TAIL_DTYPE.itemsize == 64
+DEFAULT_RECS_PER_IMAGE = 6        # capacity of the compact form: live records per image on average (typical: 1-3)
+
+
+def packed_bytes(n_alloc, capacity):
+    return n_alloc * HDR_DTYPE.itemsize + TAIL_DTYPE.itemsize + capacity * REC_DTYPE.itemsize
+
+
+def compact_records(hdr, recs, n_alloc=None, capacity=None, out=None):
+    """Dense (hdr [n,64], recs [n,max_cc,96]) -> ONE compact byte buffer [n_alloc headers | tail | capacity records]
+    (psam_compact_records): what a gather or a device->host copy moves.  hdr.reserved = index of the image's first record."""
+    L = _lib.load()
+    n, max_cc = recs.shape[0], recs.shape[1]
+    n_alloc = max(int(n_alloc or n), n)
+    capacity = int(capacity) if capacity else n_alloc * DEFAULT_RECS_PER_IMAGE
+    nb = packed_bytes(n_alloc, capacity)
+    if out is None:
+        out = torch.empty(nb, dtype=torch.uint8, device=recs.device)
+    assert out.numel() == nb
+    rc = L.psam_compact_records(_ptr(hdr), _ptr(recs), n, n_alloc, max_cc, capacity, _ptr(out), _stream())
+    _lib.check(rc, "psam_compact_records")
+    return out
+
+
+def split_packed(buf, n_alloc, capacity):
+    """views of a compact buffer: (hdr [n_alloc,64], tail [64], recs [capacity,96])"""
+    a = n_alloc * HDR_DTYPE.itemsize
+    return (buf[:a].view(n_alloc, HDR_DTYPE.itemsize), buf[a: a + TAIL_DTYPE.itemsize],
+            buf[a + TAIL_DTYPE.itemsize:].view(capacity, REC_DTYPE.itemsize))
+
+
+def decode_packed(buf, n_alloc, capacity, n_valid=None):
+    """compact buffer (device or host) -> (headers [n_valid], records [total]) as numpy structured arrays; image i owns
+    records[H['reserved'][i] : H['reserved'][i] + H['n_rec'][i]]."""
+    raw = buf.detach().cpu().numpy().tobytes()
+    a = n_alloc * HDR_DTYPE.itemsize
+    H = np.frombuffer(raw[:a], dtype=HDR_DTYPE)
+    T = np.frombuffer(raw[a: a + TAIL_DTYPE.itemsize], dtype=TAIL_DTYPE)[0]
+    if int(T["flags"]) & _lib.PACKED_OVERFLOW:
+        raise RuntimeError(f"{int(T['total'])} prompt records exceed the compact buffer's capacity {int(T['capacity'])}; "
+                           "raise recs_per_image (or read the dense records)")
+    R = np.frombuffer(raw[a + TAIL_DTYPE.itemsize:], dtype=REC_DTYPE)[: int(T["total"])]
+    return H[: (n_valid if n_valid is not None else int(T["n_img"]))], R
+
+
 def coarse_to_prompts(logits, mid, out=1024, use_cca=False, max_cc=DEFAULT_MAX_CC, max_runs=DEFAULT_MAX_RUNS,
-                      workspace=None, n_alloc=None, return_packed=False, prob_mode="softmax"):
-    """logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on device, one call.  n_alloc >= n sizes
-    the (zero-padded) output buffer, e.g. to the largest shard of a multi-GPU run."""
+                      workspace=None, n_alloc=None, return_packed=False, prob_mode="softmax", capacity=None):
+    """logits [n,2,h,w] -> (hdr uint8 [n,64], recs uint8 [n,max_cc,96]) on device, one call.  return_packed adds the
+    compact buffer (compact_records) sized for n_alloc >= n images, e.g. the largest shard of a multi-GPU run."""
     L = _lib.load()
     _need_cuda(logits)
     logits = logits.contiguous()
     n, two, h, w = logits.shape
     assert two == 2
     dev = logits.device
-    buf, hdr, recs = records_alloc(max(n_alloc or n, n), max_cc, dev)
+    _, hdr, recs = records_alloc(n, max_cc, dev)
     need = L.psam_coarse_to_prompts_workspace(n, out, max_runs, max_cc)
     ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, dev)
     rc = L.psam_coarse_to_prompts(_ptr(logits), n, h, w, int(mid), int(out), int(bool(use_cca)), PROB_MODES[prob_mode],
                                   max_cc, max_runs, _ptr(hdr), _ptr(recs), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "psam_coarse_to_prompts")
     if return_packed:
-        return hdr[:n], recs[:n], buf
-    return hdr[:n], recs[:n]
+        return hdr, recs, compact_records(hdr, recs, n_alloc=n_alloc, capacity=capacity)
+    return hdr, recs
 
 
 NEG_DTYPE = np.dtype([("pt", "<i8", 2), ("p", "<f4"), ("has", "<i4"), ("n", "<i4"), ("reserved", "<i4")])

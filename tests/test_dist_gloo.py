@@ -67,6 +67,31 @@ def _worker(rank, world, port, q_total, L, out_q):
             ok_bcast &= torch.equal(H2, H) and torch.equal(R2, R)
         else:
             ok_bcast &= H2 is None and R2 is None
+        # 4) the compact layout the engine gathers: [n_alloc headers | tail | capacity live records] per rank
+        n_alloc, cap = max(counts), max(counts) * max_cc
+        cbuf = torch.zeros(ops.packed_bytes(n_alloc, cap), dtype=torch.uint8)
+        ch, ct, cr = ops.split_packed(cbuf, n_alloc, cap)
+        first = np.concatenate([[0], np.cumsum(hdr["n_rec"])]).astype(np.int32)
+        hc = hdr.copy()
+        hc["reserved"] = first[:-1]
+        ch[:n_local] = torch.from_numpy(hc.view(np.uint8).reshape(n_local, 64).copy())
+        live = np.concatenate([recs[i, : hdr["n_rec"][i]] for i in range(n_local)]) if n_local else np.zeros(0, ops.REC_DTYPE)
+        cr[: len(live)] = torch.from_numpy(live.view(np.uint8).reshape(len(live), 96).copy())
+        tail = np.zeros(1, ops.TAIL_DTYPE)
+        tail["total"], tail["capacity"], tail["n_img"] = len(live), cap, n_local
+        ct.copy_(torch.from_numpy(tail.view(np.uint8).reshape(64).copy()))
+        H3, R3 = engine.gather_packed(cbuf, counts, ("compact", n_alloc, cap), dst=0, async_op=True).result()
+        if rank == 0:
+            Hc = ops.decode_headers(H3)
+            Rc = np.frombuffer(R3.numpy().tobytes(), dtype=ops.REC_DTYPE)
+            okc = len(Hc) == q_total * L and len(Rc) == int(Hc["n_rec"].sum())
+            for gi in range(q_total * L):
+                a, k = int(Hc["reserved"][gi]), int(Hc["n_rec"][gi])
+                okc &= k == 1 + gi % max_cc and bool((Rc["box"][a: a + k, 0] == gi).all())
+                okc &= bool(np.array_equal(Rc["label"][a: a + k], np.arange(1, k + 1)))
+            ok_bcast &= bool(okc)
+        else:
+            ok_bcast &= H3 is None and R3 is None
         if rank == 0:
             Hn, Rn = ops.decode_headers(H), ops.decode_records(R)
             ok = len(Hn) == q_total * L

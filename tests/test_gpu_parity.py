@@ -45,9 +45,15 @@ def test_alp_module_vs_reference_golden(n, capsys):
     sup_y = _t(y)[None, :, None]
     with torch.no_grad():
         if f"{n}/error" in g.files:
+            m.check_empty = True                     # the reference's behaviour: raise inside forward (one host sync)
             with pytest.raises(RuntimeError):
                 m(q, sup_x, sup_y, mode, thresh, isval=isval, val_wsize=vw, vis_sim=True)
             assert "failed to find prototypes" in capsys.readouterr().out
+            m.check_empty = False                    # default: no host sync in forward, NaN scores, the error on demand
+            pred, _, _, _ = m(q, sup_x, sup_y, mode, thresh, isval=isval, val_wsize=vw)
+            assert torch.isnan(pred).all()
+            with pytest.raises(RuntimeError):
+                m.raise_if_empty()
             return
         pred, assign, vis, grid = m(q, sup_x, sup_y, mode, thresh, isval=isval, val_wsize=vw, vis_sim=True)
     assert tuple(pred.shape) == g[f"{n}/pred_grid"].shape
@@ -585,7 +591,10 @@ def test_engine_degenerate_masks_and_queries_vs_oracle():
             np.testing.assert_allclose(logits[q, l, 1], ref[0, 0], atol=MAP_TOL, rtol=0)
     assert np.all(logits[1][~np.isnan(logits[1])] == 0.0)
     # prompts from those maps: NaN scores can never be foreground; everything still agrees with the oracle bit for bit
-    got = eng.decode(*eng.run(_t(qry)))
+    hdr, recs = eng.run(_t(qry))
+    with pytest.raises(RuntimeError):           # the reference raises for the empty 'gridconv' set; so does decode()
+        eng.decode(hdr, recs)
+    got = eng.decode(hdr, recs, on_empty_set="ignore")
     flat = logits.reshape(12, 2, h, w)
     for i in range(12):
         ref = O.coarse_to_prompts(flat[i][None], img, 256, use_cca=False, point_mode="both")
@@ -661,7 +670,7 @@ def test_graphed_volume_step_replays_equal_eager_run():
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         gs = GraphedVolumeStep(eng, sup, fg, qry)
-        assert gs.n_kernels == 2 + 3 + 3            # kernel 1 (2 launches), pack x2 + GEMM, classify + blocks + components
+        assert gs.n_kernels == 2 + 3 + 4            # kernel 1 (2 launches), pack x2 + GEMM, classify + blocks + components + compaction
         h1, r1 = gs.launch()
         h1, r1 = h1.clone(), r1.clone()
         sup.copy_(_t(vol2.sup)); fg.copy_(_t(vol2.fg)); qry.copy_(_t(vol2.qry))
@@ -758,3 +767,47 @@ def test_tokens_to_features_matches_aten_bilinear():
     assert got.shape == (2, 32, 32, 48) and np.array_equal(np.transpose(got, (0, 3, 1, 2)), ref)
     big = _t(synth.gaussian_like(4, (1, 37 * 37, 16)))
     assert ops.tokens_to_features(big).data_ptr() == big.data_ptr()              # >= 32x32 tokens: a view, no copy
+
+
+# ------------------------------------------------------------------------------ compact records
+
+def test_compact_records_equal_dense_records():
+    """psam_compact_records: headers + live records only (what gathers and host copies move) decode to the same prompts as
+    the dense [n, max_cc] arrays; too small a capacity is flagged, never silently truncated."""
+    cfg = synth.CONFIGS["cfg2_chaos_mri"]
+    vol = synth.make_volume(1234, Q=3, L=2, C=cfg["C"], h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
+    eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"])
+    eng.set_support(_t(vol.sup), _t(vol.fg))
+    logits = eng.match(_t(vol.qry))
+    n = logits.shape[0]
+    hdr, recs, packed = eng.prompts_from_logits(logits, n_alloc=n + 5, return_packed=True)
+    cap = (n + 5) * eng.recs_per_image
+    assert packed.numel() == ops.packed_bytes(n + 5, cap) == _lib.load().psam_packed_bytes(n + 5, cap)
+    H, R = ops.decode_packed(packed, n + 5, cap)
+    Hd, Rd = ops.decode_headers(hdr), ops.decode_records(recs)
+    assert len(H) == n and len(R) == int(Hd["n_rec"].sum()) > 0
+    for i in range(n):
+        k, a = int(Hd["n_rec"][i]), int(H["reserved"][i])
+        assert all(np.array_equal(H[f][i], Hd[f][i]) for f in Hd.dtype.names if f != "reserved")
+        assert R[a: a + k].tobytes() == Rd[i, :k].tobytes()
+    ph, _, pr = ops.split_packed(packed, n + 5, cap)
+    a = eng.decode(hdr, recs)
+    b = eng.decode(ph[:n], pr[: len(R)])
+    for sa, sb in zip(sum(a, []), sum(b, [])):
+        assert sa.empty == sb.empty and (sa.empty or (np.array_equal(sa.boxes, sb.boxes) and np.array_equal(sa.points, sb.points)))
+    small = ops.compact_records(hdr, recs, n_alloc=n, capacity=1)
+    with pytest.raises(RuntimeError):
+        ops.decode_packed(small, n, 1)
+
+
+def test_engine_reports_more_components_than_max_cc():
+    """more components than max_cc: the reference would prompt SAM for all of them, so decode() raises instead of
+    returning a truncated list (IMG_CC_TRUNCATED)"""
+    low = (synth.gaussian_like(5, (1, 2, 48, 48)) * 6).astype(np.float32)          # speckle: hundreds of components
+    eng = CoarseVolumeEngine((48, 48), 672, max_cc=8)
+    eng.n_labels = 1
+    hdr, recs = eng.prompts_from_logits(_t(low))
+    H = ops.decode_headers(hdr)[0]
+    assert int(H["ncc"]) > 8 and int(H["flags"]) & _lib.IMG_CC_TRUNCATED
+    with pytest.raises(RuntimeError):
+        eng.decode(hdr, recs)
