@@ -290,7 +290,9 @@ class Pipeline:
         self.NL = NL = max(1, args.lanes)
         self.engs = [CoarseVolumeEngine((h, w), cfg["img_size"], out_size=1024, val_wsize=cfg["ws"], use_cca=False,
                                         point_mode="both", match_algo=args.algo, group=groups[ln]) for ln in range(NL)]
-        self.lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]
+        self.split = bool(getattr(args, "split_streams", False)) and use_graphs
+        # split: the lane's own stream carries the match stage at high priority, the prompt stage runs on a second stream
+        self.lanes = [torch.cuda.Stream(device=dev, priority=-1 if self.split else 0) for _ in range(NL)]
         self.pending = [None] * NL
         self.replayed = 0
         self.graphs = None
@@ -299,7 +301,9 @@ class Pipeline:
             for ln in range(NL):
                 with torch.cuda.stream(self.lanes[ln]):
                     mine = [self.qvols[j] for j in range(n_rotate) if j % NL == ln] or [self.qvols[ln % n_rotate]]
-                    self.graphs.append([GraphedVolumeStep(self.engs[ln], self.sup, self.fg, qv, q_total=q_total, src=ln % world)
+                    self.graphs.append([GraphedVolumeStep(self.engs[ln], self.sup, self.fg, qv, q_total=q_total, src=ln % world,
+                                                          split_streams=self.split,
+                                                          capture_collectives=bool(getattr(args, "graph_collectives", 0)))
                                         for qv in mine])
             torch.cuda.synchronize()
 
@@ -360,6 +364,8 @@ class Pipeline:
                 if self.pending[ln] is not None:
                     self.pending[ln].wait()
                     self.pending[ln] = None
+                for gs in (self.graphs[ln] if self.graphs is not None else []):
+                    gs.join()
             torch.cuda.current_stream().wait_stream(self.lanes[ln])
 
     def sync_all(self):
@@ -573,7 +579,8 @@ def gpu_arm(args, cfg):
             with torch.cuda.stream(lanes[ln]):
                 B = lane_buf[ln]
                 B["d_sup"].copy_(sup); B["d_fg"].copy_(fg); B["d_q"].copy_(base)
-                e2e_graphs.append(GraphedVolumeStep(pipe.engs[ln], B["d_sup"], B["d_fg"], B["d_q"], q_total=q_total))
+                e2e_graphs.append(GraphedVolumeStep(pipe.engs[ln], B["d_sup"], B["d_fg"], B["d_q"], q_total=q_total,
+                                                    split_streams=pipe.split))
         pipe.sync_all()
 
     def e2e_step(i):
@@ -587,6 +594,7 @@ def gpu_arm(args, cfg):
             B["d_q"].copy_(h_q[i % N_ROTATE], non_blocking=True)
             if e2e_graphs is not None:
                 e2e_graphs[ln].launch(gather=False)
+                e2e_graphs[ln].join()
                 packed = e2e_graphs[ln].buf
             else:
                 e.set_support(B["d_sup"], B["d_fg"], broadcast=False)
@@ -753,6 +761,10 @@ def main():
                          "is a CTA that competes with the compute kernels for SMs (2 measured best at 4 and 8 GPUs)")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from Python instead of CUDA graphs")
     ap.add_argument("--lanes", type=int, default=4, help="volumes in flight per GPU (CUDA streams)")
+    ap.add_argument("--graph-collectives", type=int, default=0,
+                    help="1 (N > 1): capture the NCCL broadcast and gather into the volume's CUDA graph (one launch per volume)")
+    ap.add_argument("--split-streams", type=int, default=0,
+                    help="1: replay a volume's prompt stage on a second, lower-priority stream (engine.GraphedVolumeStep)")
     args = ap.parse_args()
     from protosam_b200 import synth
     cfg = dict(synth.CONFIGS[args.workload])

@@ -288,8 +288,17 @@ class GraphedVolumeStep:
     """
 
     def __init__(self, eng: CoarseVolumeEngine, sup_feats: torch.Tensor, fg_masks: torch.Tensor,
-                 qry_local: torch.Tensor, q_total: Optional[int] = None, src: int = 0, dst: int = 0):
+                 qry_local: torch.Tensor, q_total: Optional[int] = None, src: int = 0, dst: int = 0,
+                 split_streams: bool = False, capture_collectives: bool = False):
+        """split_streams: graph 2 is cut in two -- the match stage stays on the caller's stream, the prompt stage
+        (kernels 3a/3b, compaction, gather) is replayed on a second, lower-priority stream of this object.  The next
+        launch()'s tensor-bound match stage then does not queue behind this volume's ALU-bound prompt stage, and
+        the block scheduler places GEMM CTAs first.  join() makes the caller's stream wait for the prompt stage."""
         self.eng, self.src, self.dst = eng, src, dst
+        self.split = bool(split_streams)
+        # capture_collectives (world > 1): the broadcast and the gather are captured too, so a volume is ONE graph launch
+        # per rank -- no host round trips between the kernels and the NCCL kernels, and no Python on the critical path
+        self.one_graph = bool(capture_collectives)
         world, rank = eng._world()
         self.world, self.rank = world, rank
         L = fg_masks.shape[0]
@@ -302,6 +311,23 @@ class GraphedVolumeStep:
         torch.cuda.current_stream().synchronize()
         self.g1 = None
         k0 = ops._lib.launch_count()
+        self.one_graph = self.one_graph and world > 1 and not self.split
+        if self.one_graph:
+            self.layout = ("compact", n_alloc, n_alloc * eng.recs_per_image)
+            nb = ops.packed_bytes(n_alloc, n_alloc * eng.recs_per_image)
+            self.bucket = (list(torch.empty((world, nb), dtype=torch.uint8, device=qry_local.device).unbind(0))
+                           if rank == dst else None)
+            self.gall = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.gall):
+                eng.set_support(sup_feats, fg_masks, src=src)          # kernel 1 on `src` + the broadcast
+                self.hdr, self.recs, self.buf = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc,
+                                                                        return_packed=True)
+                dist.gather(self.buf, self.bucket, dst=dst, group=eng.group)
+            self.protos = eng.protos
+            self.n_kernels = int(ops._lib.launch_count() - k0)
+            self.n_alloc = n_alloc
+            self._pending = None
+            return
         if world == 1 or rank == src:
             self.g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g1):
@@ -310,9 +336,21 @@ class GraphedVolumeStep:
             eng.set_support(sup_feats, fg_masks, src=src, broadcast=False)     # allocates the receive table
         self.protos = eng.protos
         self.g2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g2):
-            self.hdr, self.recs, self.buf = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc,
-                                                                    return_packed=True)
+        self.g3 = None
+        if not self.split:
+            with torch.cuda.graph(self.g2):
+                self.hdr, self.recs, self.buf = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc,
+                                                                        return_packed=True)
+        else:
+            with torch.cuda.graph(self.g2):
+                self.logits = eng.match(qry_local)
+            self.g3 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g3):
+                self.hdr, self.recs, self.buf = eng.prompts_from_logits(self.logits, n_alloc=n_alloc, return_packed=True)
+            self.prompt_stream = torch.cuda.Stream(device=qry_local.device, priority=0)
+            self._match_done = torch.cuda.Event()
+            self._prompts_done = torch.cuda.Event()
+            self._prompts_recorded = False
         self.n_kernels = int(ops._lib.launch_count() - k0)      # library kernels one launch() replays
         self.n_alloc = n_alloc
         self.layout = ("compact", n_alloc, n_alloc * eng.recs_per_image)
@@ -321,6 +359,14 @@ class GraphedVolumeStep:
     def launch(self, async_gather: bool = True, gather: bool = True):
         """Enqueue one volume on the current stream.  -> this rank's (hdr, recs) device views when world == 1 or
         gather is False, else a PendingGather (or the gathered pair when async_gather is False)."""
+        if self.one_graph:
+            self.gall.replay()
+            if not gather:
+                n = self.counts[self.rank]
+                return self.hdr[:n], self.recs[:n]
+            return PendingGather(None, self.bucket, list(self.counts), self.layout, self.buf)
+        if self.split:
+            return self._launch_split(async_gather, gather)
         if self._pending is not None and isinstance(self._pending, PendingGather):
             self._pending.wait()         # graph 2 rewrites self.buf: the previous volume's gather must have read it
             self._pending = None
@@ -335,6 +381,39 @@ class GraphedVolumeStep:
         out = gather_packed(self.buf, self.counts, self.layout, dst=self.dst, group=self.eng.group, async_op=async_gather)
         self._pending = out if async_gather else None
         return out
+
+    def _launch_split(self, async_gather: bool, gather: bool):
+        cur = torch.cuda.current_stream()
+        if self._prompts_recorded:
+            cur.wait_event(self._prompts_done)       # graph 2 rewrites the logits the previous prompt stage reads
+        if self.g1 is not None:
+            self.g1.replay()
+        if self.world > 1:
+            broadcast_prototypes(self.protos, src=self.src, group=self.eng.group)
+        self.g2.replay()
+        self._match_done.record(cur)
+        out = None
+        with torch.cuda.stream(self.prompt_stream):
+            self.prompt_stream.wait_event(self._match_done)
+            if self._pending is not None and isinstance(self._pending, PendingGather):
+                self._pending.wait()                 # graph 3 rewrites self.buf: the previous gather must have read it
+                self._pending = None
+            self.g3.replay()
+            if self.world > 1 and gather:
+                out = gather_packed(self.buf, self.counts, self.layout, dst=self.dst, group=self.eng.group,
+                                    async_op=async_gather)
+                self._pending = out if async_gather else None
+            self._prompts_done.record(self.prompt_stream)
+        self._prompts_recorded = True
+        if out is None:
+            n = self.counts[self.rank]
+            return self.hdr[:n], self.recs[:n]
+        return out
+
+    def join(self):
+        """make the current stream wait for the prompt stage of the last launch() (split_streams only; a no-op otherwise)"""
+        if self.split and self._prompts_recorded:
+            torch.cuda.current_stream().wait_event(self._prompts_done)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -658,9 +658,10 @@ def test_parted_volume_engine_vs_oracle_per_slice():
                 assert np.array_equal(s.boxes, ref["bboxes"]) and np.array_equal(s.points, ref["points"])
 
 
-def test_graphed_volume_step_replays_equal_eager_run():
+@pytest.mark.parametrize("split", [False, True])
+def test_graphed_volume_step_replays_equal_eager_run(split):
     """CUDA-graph replay of a volume (engine.GraphedVolumeStep) == the eager engine, bit for bit, also after the
-    input buffers were refilled in place"""
+    input buffers were refilled in place; split: the prompt stage replayed on the step's second stream"""
     from protosam_b200.engine import GraphedVolumeStep
     cfg = synth.CONFIGS["cfg2_chaos_mri"]
     vol = synth.make_volume(5, Q=3, L=2, C=128, h=cfg["h"], w=cfg["w"], img_size=cfg["img_size"])
@@ -669,12 +670,14 @@ def test_graphed_volume_step_replays_equal_eager_run():
     sup, fg, qry = _t(vol.sup), _t(vol.fg), _t(vol.qry)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
-        gs = GraphedVolumeStep(eng, sup, fg, qry)
+        gs = GraphedVolumeStep(eng, sup, fg, qry, split_streams=split)
         assert gs.n_kernels == 2 + 3 + 4            # kernel 1 (2 launches), pack x2 + GEMM, classify + blocks + components + compaction
         h1, r1 = gs.launch()
+        gs.join()
         h1, r1 = h1.clone(), r1.clone()
         sup.copy_(_t(vol2.sup)); fg.copy_(_t(vol2.fg)); qry.copy_(_t(vol2.qry))
         h2, r2 = gs.launch()
+        gs.join()
         h2, r2 = h2.clone(), r2.clone()
     s.synchronize()
     for v, (h, r) in ((vol, (h1, r1)), (vol2, (h2, r2))):
