@@ -291,8 +291,8 @@ class Pipeline:
         self.engs = [CoarseVolumeEngine((h, w), cfg["img_size"], out_size=1024, val_wsize=cfg["ws"], use_cca=False,
                                         point_mode="both", match_algo=args.algo, group=groups[ln]) for ln in range(NL)]
         self.split = bool(getattr(args, "split_streams", False)) and use_graphs
-        # split: the lane's own stream carries the match stage at high priority, the prompt stage runs on a second stream
-        self.lanes = [torch.cuda.Stream(device=dev, priority=-1 if self.split else 0) for _ in range(NL)]
+        # split: the lane's own stream carries the match stage, the prompt stage runs on a second, higher-priority stream
+        self.lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]
         self.pending = [None] * NL
         self.replayed = 0
         self.graphs = None
@@ -756,15 +756,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-north-star-runs", action="store_true", help="skip the config-3 / config-5 sharded runs appended to the line")
     ap.add_argument("--port-only", action="store_true", help="--impl reference: time the C port even where the reference tree is mounted")
-    ap.add_argument("--nccl-channels", type=int, default=2,
-                    help="cap NCCL channels (0 = NCCL's default): the collectives move little, and every extra channel "
-                         "is a CTA that competes with the compute kernels for SMs (2 measured best at 4 and 8 GPUs)")
+    ap.add_argument("--nccl-channels", type=int, default=4,
+                    help="cap NCCL channels (0 = NCCL's default): the collectives move a few MB, and every extra channel "
+                         "is a CTA that competes with the compute kernels for SMs (4 measured best at 2 GPUs in round 2: "
+                         "0.382 ms/step vs 0.406 with 2 and 0.390 with 8)")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from Python instead of CUDA graphs")
     ap.add_argument("--lanes", type=int, default=4, help="volumes in flight per GPU (CUDA streams)")
     ap.add_argument("--graph-collectives", type=int, default=0,
                     help="1 (N > 1): capture the NCCL broadcast and gather into the volume's CUDA graph (one launch per volume)")
     ap.add_argument("--split-streams", type=int, default=0,
-                    help="1: replay a volume's prompt stage on a second, lower-priority stream (engine.GraphedVolumeStep)")
+                    help="1: replay a volume's prompt stage on a second, higher-priority stream (engine.GraphedVolumeStep)")
     args = ap.parse_args()
     from protosam_b200 import synth
     cfg = dict(synth.CONFIGS[args.workload])

@@ -35,6 +35,7 @@ SIGNATURES = {
     "psam_abi_version": (c_i, []),
     "psam_last_error": (ctypes.c_char_p, []),
     "psam_launch_count": (ctypes.c_uint64, []),
+    "psam_trace_install": (c_i, [c_p, c_sz]),
     "psam_profile_enable": (None, [c_i]),
     "psam_profile_collect": (c_i, [c_p, c_sz, c_p, c_p, c_i]),
     "psam_alp_prototypes_workspace": (c_sz, [c_i] * 7),

@@ -34,6 +34,14 @@ void max_carveout_once(const void* kernel, bool* done)
     if (!off) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+static std::vector<void (*)(TraceRec*)>& trace_setters()
+{
+    static std::vector<void (*)(TraceRec*)> v;
+    return v;
+}
+
+void trace_register(void (*setter)(TraceRec*)) { trace_setters().push_back(setter); }
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // ---- optional per-kernel timing: one CUDA event pair around every launch of this library ----
@@ -73,6 +81,21 @@ static_assert(sizeof(psam_image_hdr) == 64, "psam_image_hdr layout is part of th
 extern "C" int psam_abi_version(void) { return PSAM_ABI_VERSION; }
 extern "C" const char* psam_last_error(void) { return psam::g_err; }
 extern "C" uint64_t psam_launch_count(void) { return psam::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int psam_trace_install(void* buffer, size_t bytes)
+{
+    using namespace psam;
+    TraceRec* buf = static_cast<TraceRec*>(buffer);
+    if (buf) {
+        if (bytes < 2 * sizeof(TraceRec)) { set_error("psam_trace_install: buffer too small"); return PSAM_ERR_ARG; }
+        TraceRec hdr;
+        memset(&hdr, 0, sizeof(hdr));
+        hdr.t1 = bytes / sizeof(TraceRec);
+        if (cudaMemcpy(buf, &hdr, sizeof(hdr), cudaMemcpyHostToDevice) != cudaSuccess) return PSAM_ERR_LAUNCH;
+    }
+    for (auto f : trace_setters()) f(buf);
+    return cudaDeviceSynchronize() == cudaSuccess ? PSAM_OK : PSAM_ERR_LAUNCH;
+}
 
 extern "C" void psam_profile_enable(int on)
 {

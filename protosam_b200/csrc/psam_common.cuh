@@ -79,6 +79,47 @@ struct Carver {
     size_t used() const { return align_up(off, 256); }
 };
 
+// ---- optional CTA-level trace (tools/trace_timeline.py): while a trace buffer is installed (psam_trace_install), the big
+// kernels record, per CTA, the SM it ran on and its start / end time (globaltimer, ns).  Every translation unit has its
+// own copy of the pointer; psam_trace_install sets all of them.  One predictable branch per CTA when off. ----
+struct TraceRec {
+    unsigned long long t0, t1;
+    unsigned int smid, kernel, cta, pad;
+};
+static __device__ TraceRec* g_trace_buf = nullptr;     // [0] is the header: t0 = number of records taken so far, t1 = capacity
+void trace_register(void (*setter)(TraceRec*));
+
+__device__ __forceinline__ unsigned long long trace_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// call from ONE thread at the start of a CTA; returns the record (or nullptr) to hand to trace_end
+__device__ __forceinline__ TraceRec* trace_begin(unsigned int kernel)
+{
+    TraceRec* buf = g_trace_buf;
+    if (buf == nullptr) return nullptr;
+    const unsigned long long slot = atomicAdd(&buf[0].t0, 1ull) + 1ull;
+    if (slot >= buf[0].t1) return nullptr;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    TraceRec* r = buf + slot;
+    r->smid = smid; r->kernel = kernel; r->cta = blockIdx.x + gridDim.x * blockIdx.y; r->pad = 0;
+    r->t0 = trace_now(); r->t1 = 0;
+    return r;
+}
+
+__device__ __forceinline__ void trace_end(TraceRec* r)
+{
+    if (r) r->t1 = trace_now();
+}
+
+#define PSAM_TRACE_TU()                                                                     \
+    static void trace_set_this_tu(psam::TraceRec* p) { cudaMemcpyToSymbol(psam::g_trace_buf, &p, sizeof(p)); } \
+    static const int trace_registered__ = (psam::trace_register(trace_set_this_tu), 0)
+
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v)
 {

@@ -16,6 +16,7 @@
 //
 // Roofline: latency/HBM bound, small: algorithmic bytes per image = out^2/8 (bits) + 4*n_fg
 // (p_fg under the mask) read + 96*ncc written.
+#include <cstdlib>
 #include <cstring>
 
 #include "psam_common.cuh"
@@ -23,7 +24,10 @@
 
 namespace psam {
 
-constexpr int CT = 1024;         // threads per CTA
+constexpr int CT = 512;          // threads per CTA: the kernel is latency-bound, so per image 512 threads cost little
+                                 // time, and a 512-thread, 24 K-register, ~13 KB-shared-memory CTA fits on an SM
+                                 // beside a GEMM CTA and two block-kernel CTAs of other volumes (1024 threads did not)
+constexpr int MAXR = 2048;       // components ranked through the shared-memory key list (more: global bitmap path)
 constexpr int MAX_OUT = 1024;    // image side supported by the static tables below
 constexpr int KEY_WORDS = (MAX_OUT / 2) * (MAX_OUT / 2) / 32;  // bitmap over 2x2 blocks
 
@@ -45,6 +49,7 @@ struct CompParams {
     uint16_t *run_s, *run_e, *run_y;
     int32_t* parent;
     uint32_t* minkey;
+    uint32_t* gkeys;         // per CTA: 2 * KEY_WORDS words (bitmap + prefix of the > MAXR-components path)
     unsigned long long* sump;
     int32_t* rank;
     Acc* acc;
@@ -172,9 +177,9 @@ __device__ __forceinline__ void run_stats_thread(const uint32_t* __restrict__ bi
 __global__ void __maxnreg__(48) k_components(CompParams P)
 {
     __shared__ int s_rowstart[MAX_OUT + 1];
-    extern __shared__ uint32_t s_dyn[];          // 2 * KEY_WORDS words (64 KB, opt-in)
-    uint32_t* s_bitmap = s_dyn;
-    uint32_t* s_prefix = s_dyn + KEY_WORDS;
+    __shared__ __align__(8) uint32_t s_keys[MAXR];        // first-block keys of the components; later the topk scratch
+    uint32_t* s_bitmap = P.gkeys + (size_t)blockIdx.x * 2 * KEY_WORDS;   // global fallback for > MAXR components
+    uint32_t* s_prefix = s_bitmap + KEY_WORDS;
     __shared__ int s_scan[32];
     __shared__ unsigned long long s_red64[32];
     __shared__ int s_misc[16];
@@ -191,6 +196,7 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
     unsigned long long* sump = P.sump + so;
     int32_t* rank = P.rank + so;
     Acc* acc = P.acc + (size_t)blockIdx.x * P.max_cc;
+    TraceRec* tr = tid == 0 ? trace_begin(4) : nullptr;
 
     for (int img = blockIdx.x; img < P.n_img; img += gridDim.x) {
         const uint32_t* bits = P.maskbits + (size_t)img * out * wpr;
@@ -205,8 +211,7 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
         unsigned int bminx = 0xffffffffu, bminy = 0xffffffffu, bmaxx = 0, bmaxy = 0;
         unsigned long long bsx = 0, bsy = 0;
         int bany = 0;
-        if (tid <= MAX_OUT) s_rowstart[tid] = 0;
-        if (tid == 0) s_rowstart[MAX_OUT] = 0;
+        for (int i = tid; i <= MAX_OUT; i += CT) s_rowstart[i] = 0;
         __syncthreads();
         for (int yb = wid; yb < out; yb += 4 * (CT / 32)) {
           uint32_t wq[4];
@@ -271,18 +276,31 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
 
         // ---- S2: exclusive scan of the per-row run counts --------------------------------
         {
-            const int v = tid < out ? s_rowstart[tid] : 0;
+            constexpr int RP = (MAX_OUT + CT - 1) / CT;          // consecutive rows per thread
+            int cnt[RP], v = 0;
+#pragma unroll
+            for (int k = 0; k < RP; ++k) {
+                const int y = tid * RP + k;
+                cnt[k] = y < out ? s_rowstart[y] : 0;
+                v += cnt[k];
+            }
             const int ex = warp_excl_scan_i(v, lane);
             if (lane == 31) s_scan[wid] = ex + v;
             __syncthreads();
             if (wid == 0) {
-                const int t = s_scan[lane];
+                const int t = lane < CT / 32 ? s_scan[lane] : 0;
                 const int e2 = warp_excl_scan_i(t, lane);
                 s_scan[lane] = e2;
                 if (lane == 31) s_misc[6] = e2 + t;
             }
             __syncthreads();
-            if (tid < out) s_rowstart[tid] = s_scan[wid] + ex;
+            int run = s_scan[wid] + ex;
+#pragma unroll
+            for (int k = 0; k < RP; ++k) {
+                const int y = tid * RP + k;
+                if (y < out) s_rowstart[y] = run;
+                run += cnt[k];
+            }
             if (tid == 0) s_rowstart[out] = s_misc[6];
             __syncthreads();
         }
@@ -351,7 +369,7 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
             }
           }
         }
-        for (int i = tid; i < key_words; i += CT) s_bitmap[i] = 0u;
+        if (tid == 0) s_misc[10] = 0;
         __syncthreads();
 
         // ---- S4: connect runs of adjacent rows that touch (8-connectivity) ----------------------
@@ -402,11 +420,31 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
             atomicMin(&minkey[parent[i]], key);
         }
         __syncthreads();
-        // ---- S7-S9: OpenCV label = 1 + rank of that block among all components' first blocks
+        // ---- S7-S9: OpenCV label = 1 + rank of that block among all components' first blocks.  A 2x2 block holds pixels
+        // of one component only, so the keys are distinct.  Up to MAXR components: their keys are collected in shared
+        // memory and every root counts the smaller ones; beyond that (speckle): bitmap over the blocks + popcount prefix
+        // in this CTA's global scratch.
         for (int i = tid; i < total; i += CT)
-            if (parent[i] == i) atomicOr(&s_bitmap[minkey[i] >> 5], 1u << (minkey[i] & 31));
+            if (parent[i] == i) {
+                const int slot = atomicAdd(&s_misc[10], 1);
+                if (slot < MAXR) s_keys[slot] = minkey[i];
+            }
         __syncthreads();
-        {
+        const int ncc = s_misc[10];
+        if (ncc <= MAXR) {
+            for (int i = tid; i < total; i += CT)
+                if (parent[i] == i) {
+                    const uint32_t k = minkey[i];
+                    int r = 0;
+                    for (int j = 0; j < ncc; ++j) r += s_keys[j] < k;
+                    rank[i] = r;
+                }
+        } else {
+            for (int i = tid; i < key_words; i += CT) s_bitmap[i] = 0u;
+            __syncthreads();
+            for (int i = tid; i < total; i += CT)
+                if (parent[i] == i) atomicOr(&s_bitmap[minkey[i] >> 5], 1u << (minkey[i] & 31));
+            __syncthreads();
             const int per = (key_words + CT - 1) / CT;
             const int w0 = tid * per;
             int local = 0;
@@ -416,23 +454,21 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
             if (lane == 31) s_scan[wid] = ex + local;
             __syncthreads();
             if (wid == 0) {
-                const int t = s_scan[lane];
+                const int t = lane < CT / 32 ? s_scan[lane] : 0;
                 const int e2 = warp_excl_scan_i(t, lane);
                 s_scan[lane] = e2;
-                if (lane == 31) s_misc[7] = e2 + t;
             }
             __syncthreads();
             int run = s_scan[wid] + ex;
             for (int k = 0; k < per; ++k)
                 if (w0 + k < key_words) { s_prefix[w0 + k] = run; run += __popc(s_bitmap[w0 + k]); }
             __syncthreads();
+            for (int i = tid; i < total; i += CT)
+                if (parent[i] == i) {
+                    const uint32_t k = minkey[i];
+                    rank[i] = (int)s_prefix[k >> 5] + __popc(s_bitmap[k >> 5] & ((1u << (k & 31)) - 1u));
+                }
         }
-        const int ncc = s_misc[7];
-        for (int i = tid; i < total; i += CT)
-            if (parent[i] == i) {
-                const uint32_t k = minkey[i];
-                rank[i] = (int)s_prefix[k >> 5] + __popc(s_bitmap[k >> 5] & ((1u << (k & 31)) - 1u));
-            }
         __syncthreads();
 
         // ---- S10: use_cca -- exact per-component sums of p_fg, keep the largest ------------
@@ -444,22 +480,24 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
                 if (lane == 0) atomicAdd(&sump[parent[i]], acc_p);
             }
             __syncthreads();
-            // strictly largest confidence, first label on ties (util/utils.py:511-515)
+            // strictly largest confidence, first label on ties (util/utils.py:511-515): the largest exact sum, then the
+            // smallest rank among the components that reach it (two reductions: a packed (sum << 20 | rank) key would
+            // overflow 64 bits for a full-frame component, sum = 2^44)
             unsigned long long best = 0;
             for (int i = tid; i < total; i += CT)
-                if (parent[i] == i) {
-                    const unsigned long long k = (sump[i] << 20) | (unsigned long long)(0xFFFFF - rank[i]);
-                    best = max(best, k);
-                }
+                if (parent[i] == i) best = max(best, sump[i]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) best = max(best, shfl_xor_u64(best, o));
             if (lane == 0) s_red64[wid] = best;
+            if (tid == 0) s_misc[9] = 0x7fffffff;
             __syncthreads();
             best = 0;
             for (int k = 0; k < CT / 32; ++k) best = max(best, s_red64[k]);
+            const unsigned long long best_sum = best;
+            for (int i = tid; i < total; i += CT)
+                if (parent[i] == i && sump[i] == best_sum) atomicMin(&s_misc[9], rank[i]);
             __syncthreads();
-            const int best_rank = 0xFFFFF - (int)(best & 0xFFFFF);
-            const unsigned long long best_sum = best >> 20;
+            const int best_rank = s_misc[9];
             unsigned long long second = 0;
             for (int i = tid; i < total; i += CT)
                 if (parent[i] == i) {
@@ -535,7 +573,7 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
         // under it belongs to the component) and, only if the maximum is attained more than once, replays
         // libstdc++'s nth_element on them.  A unique maximum needs no replay: every algorithm returns it.
         {
-            TK* q = reinterpret_cast<TK*>(s_prefix) + wid * 64;         // s_prefix is free again: 32 warps x 64 x 8 B = 16 KB
+            TK* q = reinterpret_cast<TK*>(s_keys) + wid * 64;           // the key list is free again: 16 warps x 64 x 8 B = 8 KB
             for (int r = wid; r < n_rec; r += CT / 32) {
                 const Acc a = acc[r];
                 if (a.area >= 64) continue;
@@ -598,6 +636,7 @@ __global__ void __maxnreg__(48) k_components(CompParams P)
         }
         __syncthreads();
     }
+    trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -659,6 +698,7 @@ __global__ void __launch_bounds__(1024) k_compact_records(const psam_image_hdr* 
     psam_packed_tail* tail = reinterpret_cast<psam_packed_tail*>(packed + (size_t)n_alloc * sizeof(psam_image_hdr));
     psam_prompt_rec* orec = reinterpret_cast<psam_prompt_rec*>(tail + 1);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    TraceRec* tr = tid == 0 ? trace_begin(9) : nullptr;
     if (tid == 0) s_base = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n_alloc; i0 += 1024) {
@@ -701,12 +741,14 @@ __global__ void __launch_bounds__(1024) k_compact_records(const psam_image_hdr* 
         tail->n_img = n_img;
         for (int k = 0; k < 12; ++k) tail->reserved[k] = 0;
     }
+    trace_end(tr);
 }
 
 }  // namespace psam
 
 using namespace psam;
 
+PSAM_TRACE_TU();
 extern "C" size_t psam_packed_bytes(int n_alloc, int capacity)
 {
     if (n_alloc <= 0 || capacity < 0) return 0;
@@ -732,7 +774,7 @@ static int comp_grid(int n_img)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return n_img < sms ? n_img : sms;
+    return n_img < 2 * sms ? n_img : 2 * sms;      // up to two 512-thread CTAs per SM
 }
 
 static size_t comp_scratch_bytes(int ctas, int max_runs, int max_cc)
@@ -744,6 +786,7 @@ static size_t comp_scratch_bytes(int ctas, int max_runs, int max_cc)
     b += align_up(sizeof(uint32_t) * (size_t)ctas * max_runs, 256);
     b += align_up(sizeof(unsigned long long) * (size_t)ctas * max_runs, 256);
     b += align_up(sizeof(Acc) * (size_t)ctas * max_cc, 256);
+    b += align_up(sizeof(uint32_t) * (size_t)ctas * 2 * KEY_WORDS, 256);
     return b + 256;
 }
 
@@ -783,20 +826,14 @@ extern "C" int psam_components(const uint32_t* maskbits, const float* p_fg, cons
     P.minkey = cv.take<uint32_t>(n);
     P.sump = cv.take<unsigned long long>(n);
     P.acc = cv.take<Acc>((size_t)ctas * max_cc);
+    P.gkeys = cv.take<uint32_t>((size_t)ctas * 2 * KEY_WORDS);
     if (labels_out) {
         cudaError_t e = cudaMemsetAsync(labels_out, 0, sizeof(int32_t) * (size_t)n_img * out * out, stream);
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return PSAM_ERR_LAUNCH; }
     }
-    const int dyn = 2 * KEY_WORDS * (int)sizeof(uint32_t);
-    static bool attr_done_dev[64] = {};
-    int cur_dev = 0;
-    cudaGetDevice(&cur_dev);
-    bool& attr_done = attr_done_dev[cur_dev >= 0 && cur_dev < 64 ? cur_dev : 0];
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PSAM_ERR_LAUNCH; }
-        attr_done = true;
-    }
+    const int dyn = 0;
+    static const bool skip = getenv("PSAM_EXPERIMENT_SKIP_COMPONENTS") != nullptr;   // timing experiments only: no records
+    if (skip) return PSAM_OK;
     PSAM_PROF_BEGIN(stream);
     PSAM_MAX_CARVEOUT(k_components);
     k_components<<<ctas, CT, dyn, stream>>>(P);

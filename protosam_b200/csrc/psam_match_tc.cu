@@ -232,11 +232,13 @@ __global__ void __launch_bounds__(256) k_pack_query(const float* __restrict__ qr
 {
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int tile = g >> 7, grp = (g & 127) >> 3, r = g & 7;
+    TraceRec* tr = (threadIdx.x == 0 && (blockIdx.x & 15) == 0) ? trace_begin(2) : nullptr;   // every 16th CTA
     const bool valid = g < R;
     const float* src = valid ? qry + (size_t)(g / HW) * slice_stride + (size_t)(g % HW) * row_stride : qry;
     uint8_t* group0 = a_img + ((size_t)tile * KB * 16 + grp) * GROUP_BYTES;
     const float ssq = pack_row(src, valid, C, KB, lane, group0, (size_t)16 * GROUP_BYTES, r);
     if (lane == 0) scale[g] = valid ? 20.0f / fmaxf(sqrtf(ssq), 1e-4f) : 0.f;
+    trace_end(tr);
 }
 
 // b_img[kb][G groups][2048 B] over the concatenated, 16-padded prototype columns of all sets.
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    TraceRec* tr = threadIdx.x == 0 ? trace_begin(1) : nullptr;
 
     if (threadIdx.x == 0) {
         int T = 0;
@@ -586,6 +589,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
 
     tc_fence_before();
     __syncthreads();
+    trace_end(tr);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -624,6 +628,7 @@ static Layout make_layout(int Q, int HW, int C, int nsets, int cap_rows)
 
 }  // namespace tc
 
+PSAM_TRACE_TU();
 bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want_sims)
 {
     (void)cap_rows;

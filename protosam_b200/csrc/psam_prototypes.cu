@@ -299,12 +299,14 @@ struct ProtoArgs {
 __global__ void __launch_bounds__(256) k_proto_stage1(ProtoArgs a, SetModes modes)
 {
     const int set = blockIdx.y;
+    TraceRec* tr = (threadIdx.x == 0 && (blockIdx.x & 7) == 0) ? trace_begin(6) : nullptr;
     if (blockIdx.x == 0)
         pool_mask_body(set, a.sup_y, modes, a.S, a.h, a.w, a.kh, a.kw, a.akh, a.akw, a.thresh, a.pooled, a.survive, a.rowidx,
                        a.ysum, a.counts, a.eff_modes, a.status, a.plocal);
     else
         global_partial_body((blockIdx.x - 1) % a.h, (blockIdx.x - 1) / a.h, set, a.sup_x, a.xs_s, a.xs_c, a.xs_y, a.xs_x,
                             a.sup_y, modes, a.S, a.C, a.h, a.w, a.partial);
+    trace_end(tr);
 }
 
 __global__ void __launch_bounds__(256) k_proto_stage2(ProtoArgs a, SetModes modes, int N)
@@ -312,12 +314,14 @@ __global__ void __launch_bounds__(256) k_proto_stage2(ProtoArgs a, SetModes mode
     extern __shared__ __align__(16) float s_stage[];
     __shared__ __align__(8) uint64_t s_bar;
     const int set = blockIdx.y;
+    TraceRec* tr = (threadIdx.x == 0 && (blockIdx.x & 15) == 0) ? trace_begin(7) : nullptr;
     if ((int)blockIdx.x < N)
         pool_feat_body(blockIdx.x, set, a.sup_x, a.xs_s, a.xs_c, a.xs_y, a.xs_x, a.rowidx, a.S, a.C, a.h, a.w, a.kh, a.kw,
                        a.cap_rows, a.protos, s_stage, &s_bar);
     else
         global_final_body(blockIdx.x - N, set, a.partial, a.ysum, a.eff_modes, a.plocal, modes, a.S, a.C, a.h, a.cap_rows,
                           a.protos);
+    trace_end(tr);
 }
 
 // ------------------------------------------------------------------------------------
@@ -477,6 +481,7 @@ __global__ void __launch_bounds__(256) k_tokens_bilinear(const float* __restrict
 
 using namespace psam;
 
+PSAM_TRACE_TU();
 extern "C" int psam_tokens_to_features(const float* tokens, int B, int h, int w, int C, int oh, int ow, float* out,
                                        psam_stream_t stream_)
 {

@@ -291,9 +291,14 @@ class GraphedVolumeStep:
                  qry_local: torch.Tensor, q_total: Optional[int] = None, src: int = 0, dst: int = 0,
                  split_streams: bool = False, capture_collectives: bool = False):
         """split_streams: graph 2 is cut in two -- the match stage stays on the caller's stream, the prompt stage
-        (kernels 3a/3b, compaction, gather) is replayed on a second, lower-priority stream of this object.  The next
-        launch()'s tensor-bound match stage then does not queue behind this volume's ALU-bound prompt stage, and
-        the block scheduler places GEMM CTAs first.  join() makes the caller's stream wait for the prompt stage."""
+        (kernels 3a/3b, compaction, gather) is replayed on a second, HIGHER-priority stream of this object.  The GPU's
+        work distributor hands out CTAs kernel by kernel in arrival order within a priority level: with several volumes
+        in flight the GEMM grids of the other lanes (each needs every SM) queue up ahead of this volume's prompt kernels,
+        which then wait although their CTAs would fit beside a resident GEMM CTA (measured with tools/trace_timeline.py:
+        the lanes run phase-locked, four GEMMs back to back, then four prompt stages).  On a higher-priority stream the
+        prompt kernels are dispatched as soon as they are ready, beside the GEMM of the next volume.  The next launch()'s
+        match stage also no longer queues behind this volume's prompt stage.  join() makes the caller's stream wait
+        for the prompt stage."""
         self.eng, self.src, self.dst = eng, src, dst
         self.split = bool(split_streams)
         # capture_collectives (world > 1): the broadcast and the gather are captured too, so a volume is ONE graph launch
@@ -347,7 +352,7 @@ class GraphedVolumeStep:
             self.g3 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g3):
                 self.hdr, self.recs, self.buf = eng.prompts_from_logits(self.logits, n_alloc=n_alloc, return_packed=True)
-            self.prompt_stream = torch.cuda.Stream(device=qry_local.device, priority=0)
+            self.prompt_stream = torch.cuda.Stream(device=qry_local.device, priority=-1)
             self._match_done = torch.cuda.Event()
             self._prompts_done = torch.cuda.Event()
             self._prompts_recorded = False
