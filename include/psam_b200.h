@@ -64,7 +64,8 @@ uint64_t psam_launch_count(void);
  * order, their newline-separated names, accumulated milliseconds and launch counts. */
 /* Optional CTA-level trace for timeline analysis (tools/trace_timeline.py): install a zero-initialised device buffer and
  * the big kernels record, per CTA, {start ns, end ns, SM id, kernel id, CTA index} (32-byte records; record 0 is the
- * header: t0 = records taken, t1 = capacity).  NULL uninstalls.  Synchronises the device; not for use inside graphs
+ * header: t0 = records taken, t1 = capacity).  NULL uninstalls.  Needs a library built with `make TRACE=1`
+ * (PSAM_ERR_UNSUPPORTED otherwise).  Synchronises the device; not for use inside graphs
  * capture.  Kernel ids: 1 k_match_tc, 2 k_pack_query, 3 k_blocks_warp, 4 k_components, 5 k_classify_blocks,
  * 6 k_proto_stage1, 7 k_proto_stage2, 8 k_pack_protos, 9 k_compact_records. */
 int psam_trace_install(void* device_buffer, size_t bytes);

@@ -85,6 +85,10 @@ extern "C" uint64_t psam_launch_count(void) { return psam::g_launches.load(std::
 extern "C" int psam_trace_install(void* buffer, size_t bytes)
 {
     using namespace psam;
+    if (!kTraceCompiled) {
+        set_error("psam_trace_install: the library was built without kernel tracing (make -C protosam_b200/csrc TRACE=1)");
+        return PSAM_ERR_UNSUPPORTED;
+    }
     TraceRec* buf = static_cast<TraceRec*>(buffer);
     if (buf) {
         if (bytes < 2 * sizeof(TraceRec)) { set_error("psam_trace_install: buffer too small"); return PSAM_ERR_ARG; }

@@ -96,7 +96,9 @@ __device__ __forceinline__ unsigned long long trace_now()
     return t;
 }
 
-// call from ONE thread at the start of a CTA; returns the record (or nullptr) to hand to trace_end
+// call from ONE thread at the start of a CTA; returns the record (or nullptr) to hand to trace_end.  Compiled in only
+// with -DPSAM_TRACE_KERNELS (make TRACE=1): the production library carries no trace code in its kernels.
+#ifdef PSAM_TRACE_KERNELS
 __device__ __forceinline__ TraceRec* trace_begin(unsigned int kernel)
 {
     TraceRec* buf = g_trace_buf;
@@ -115,6 +117,12 @@ __device__ __forceinline__ void trace_end(TraceRec* r)
 {
     if (r) r->t1 = trace_now();
 }
+constexpr bool kTraceCompiled = true;
+#else
+__device__ __forceinline__ TraceRec* trace_begin(unsigned int) { return nullptr; }
+__device__ __forceinline__ void trace_end(TraceRec*) {}
+constexpr bool kTraceCompiled = false;
+#endif
 
 #define PSAM_TRACE_TU()                                                                     \
     static void trace_set_this_tu(psam::TraceRec* p) { cudaMemcpyToSymbol(psam::g_trace_buf, &p, sizeof(p)); } \

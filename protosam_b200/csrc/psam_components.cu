@@ -721,10 +721,18 @@ __global__ void __launch_bounds__(1024) k_compact_records(const psam_image_hdr* 
             h.reserved = first;
             ohdr[i] = h;
         }
-        // one warp per image of this chunk copies the image's records
+        // images with a few records (the usual 1-3): their thread copies them, all loads of the CTA in flight at once;
+        // images with many: one warp per image, 96 B = 6 x 16 B per lane
+        if (n > 0 && n <= 8) {
+            const uint4* src = reinterpret_cast<const uint4*>(recs + (size_t)i * max_cc);
+            uint4* dst = reinterpret_cast<uint4*>(orec + first);
+            const int nk = min(n, max(capacity - first, 0)) * 6;
+            for (int k = 0; k < nk; ++k) dst[k] = src[k];
+        }
         for (int j = 0; j < 32; ++j) {
-            const int img = i0 + wid * 32 + j;
             const int nj = __shfl_sync(0xffffffffu, n, j), fj = __shfl_sync(0xffffffffu, first, j);
+            if (nj <= 8) continue;
+            const int img = i0 + wid * 32 + j;
             const uint4* src = reinterpret_cast<const uint4*>(recs + (size_t)img * max_cc);
             uint4* dst = reinterpret_cast<uint4*>(orec + fj);
             for (int k = lane; k < nj * 6; k += 32)

@@ -370,7 +370,10 @@ POINT_MODE_IDS = {"conf": 0, "centroid": 1, "both": 2}
 def records_to_sam(hdr, recs, point_mode="both", original_size=(1024, 1024), target_length=1024):
     """Device records -> (points [n,max_cc,npts,2] f32, labels [n,max_cc,npts] i32, boxes [n,max_cc,4] f32) in SAM's
     input frame, ready for SamPredictor.predict_torch (one call per image with batch = its n_rec components).  No host
-    round trip: the prompts never leave the device."""
+    round trip: the prompts never leave the device.  Slots beyond an image's n_rec are zero; an image whose header
+    carries IMG_CC_TRUNCATED (more components than max_cc) or IMG_RUN_OVERFLOW has FEWER prompts here than the reference
+    would issue -- the flags stay in hdr[:, 12:16] (int32 `flags`) for the caller to test on the device, and
+    CoarseVolumeEngine.decode() raises on them."""
     L = _lib.load()
     hdr, recs = hdr.contiguous(), recs.contiguous()
     n, max_cc = recs.shape[0], recs.shape[1]

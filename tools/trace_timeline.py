@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """CTA-level timeline of the volume pipeline (psam_trace_install): which kernel's CTAs sit on which SM when.
 
+    make -C protosam_b200/csrc clean && make -C protosam_b200/csrc TRACE=1 -j4        (trace hooks are compiled out by default)
     python tools/trace_timeline.py run  [--steps 12] [--lanes 4] -> gpurun_out/trace.npy   (needs a GPU)
     python tools/trace_timeline.py show gpurun_out/trace.npy                                  (anywhere)
 
