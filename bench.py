@@ -675,6 +675,8 @@ def gpu_arm(args, cfg):
     n_cc = int(H["ncc"][: n_img].sum()) if H is not None else 0
     flops_match = 2.0 * q_local * h * w * C * sumP             # algorithmic: 2*HW*C*sum(P) per slice
     model = {   # kernel -> (bound, algorithmic work per launch, note)
+        "k_match_ts": ("tensor", flops_match, "2*HW*C*sum(P) per slice; executed = 3x (split-bf16 passes); fp32 query "
+                       "converted inside the GEMM, A operand in TMEM"),
         "k_match_tc": ("tensor", flops_match, "2*HW*C*sum(P) per slice; executed = 3x (split-bf16 passes)"),
         "k_match_simt": ("tensor", flops_match, "2*HW*C*sum(P) per slice on CUDA cores"),
         "k_blocks_warp": ("hbm", n_img * (8.0 * h * w + out * out / 8.0) + 4.0 * n_fg,
@@ -685,7 +687,7 @@ def gpu_arm(args, cfg):
                          "per image: out^2/8 mask bits + 4*n_fg probabilities + 96 B per component (latency-bound integer work)"),
         "k_pack_query": ("hbm", 8.0 * q_local * h * w * C, "4*C*HW read + 4*C*HW operand image written per slice"),
     }
-    dom = max(prof, key=lambda k: prof[k][0]) if prof else "k_match_tc"
+    dom = max(prof, key=lambda k: prof[k][0]) if prof else "k_match_ts"
     ms_dom, n_dom = prof.get(dom, (ms_match, 1))
     n_dom = max(n_dom, 1)
     bound, work, note = model.get(dom, ("hbm", 0.0, "no model"))
@@ -701,18 +703,20 @@ def gpu_arm(args, cfg):
             "kernels_ms_per_step": {k: round(v[0], 5) for k, v in prof.items()},
             "match_stage_ms": ms_match, "prompt_stage_ms": ms_prompt, "volume_latency_ms": ms_volume,
             "issue_slot_busy_pct": traffic_tab.get("issue_slot_busy_pct", {})}
-    if "k_match_tc" in prof:
-        t = prof["k_match_tc"][0] * 1e-3
-        mk = {"kernel": "k_match_tc", "bound": "tensor", "achieved": flops_match / t / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+    gemm = next((k for k in ("k_match_ts", "k_match_tc") if k in prof), None)
+    if gemm:
+        t = prof[gemm][0] * 1e-3
+        mk = {"kernel": gemm, "bound": "tensor", "achieved": flops_match / t / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
               "frac": flops_match / t / 1e12 / peak_tf, "executed_frac": 3 * flops_match / t / 1e12 / peak_tf,
-              "ceiling_frac": 1.0 / 3.0, "traffic": traffic_tab.get("k_match_tc"), "ms_per_launch": prof["k_match_tc"][0]}
-        if dom == "k_match_tc":
+              "ceiling_frac": 1.0 / 3.0, "traffic": traffic_tab.get(gemm), "ms_per_launch": prof[gemm][0]}
+        if dom == gemm:
             roof["executed_frac"], roof["ceiling_frac"] = mk["executed_frac"], mk["ceiling_frac"]
         else:
             roof["match_kernel"] = mk
         # the fused ALP path of north_star = kernels 1 + 2 (prototypes, operand images, contraction + softmax epilogue)
         alp = sum(v[0] for k, v in prof.items() if k.startswith(("k_proto_stage", "k_pack_", "k_match_")))
-        roof["alp_path"] = {"kernels": "k_proto_stage1/2 + k_pack_protos + k_pack_query + k_match_tc", "ms_per_step": alp,
+        roof["alp_path"] = {"kernels": " + ".join(k for k in prof if k.startswith(("k_proto_stage", "k_pack_", "k_match_"))),
+                            "ms_per_step": alp,
                             "achieved": flops_match / (alp * 1e-3) / 1e12, "unit": "TFLOP/s",
                             "frac": flops_match / (alp * 1e-3) / 1e12 / peak_tf, "ceiling_frac": 1.0 / 3.0}
 

@@ -26,6 +26,8 @@ int launch_match_simt(const MatchParams& p, cudaStream_t stream);
 // tcgen05 tensor-core variant (psam_match_tc.cu)
 bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want_sims);
 // fused = the GEMM converts the fp32 query rows itself (no packed query image, no separate pass over the query)
+// the fused variant additionally needs dense slices (one 2-D tensor map over all query rows)
+bool match_ts_supported(const MatchParams& p);
 size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fused);
 int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, bool fused, cudaStream_t stream);
 

@@ -22,9 +22,10 @@
 
 #include "psam_match.cuh"
 
-// which tensor-core variant algo = 0 (auto) takes
+// algo = 0 (auto) takes the fused tensor-core variant (query converted inside the GEMM, A operand in TMEM) whenever the
+// slices are dense, else the packed-operand variant; -DPSAM_AUTO_FUSED=0 restores the packed variant as the default
 #ifndef PSAM_AUTO_FUSED
-#define PSAM_AUTO_FUSED 0
+#define PSAM_AUTO_FUSED 1
 #endif
 
 namespace psam {
@@ -231,7 +232,7 @@ extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t ro
     // auto: tensor cores whenever the variant applies (the raw-similarity dump for visualisation and channel
     // counts that are not a multiple of 8 stay on the CUDA-core kernel) and the caller sized the workspace for it
     if (algo == 0 && match_tc_supported(Q, HW, C, nsets, cap_rows, sims != nullptr) && workspace) {
-        if (PSAM_AUTO_FUSED && workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, true))
+        if (PSAM_AUTO_FUSED && match_ts_supported(p) && workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, true))
             return launch_match_tc(p, workspace, workspace_bytes, true, stream);
         if (workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, false))
             return launch_match_tc(p, workspace, workspace_bytes, false, stream);

@@ -22,22 +22,29 @@
 // Structure (one persistent CTA per SM):
 //   k_pack_protos  prototype rows of all sets, concatenated (each set padded to 16 columns) so one B matrix serves
 //                  every set -> bf16 hi/lo planes already in the swizzled K-major layout the MMA reads.
-//   k_pack_query   [algo 2] the same for the query rows, per (128-row tile, 64-channel block), plus the per-row
+//   k_pack_query   [algo 2] the same for the query rows, per (128-row tile, 32-channel block), plus the per-row
 //                  scale 20/max(|q|,1e-4).
-//   k_match_tc     warp 0: one thread streams operand blocks global -> shared with cp.async.bulk
-//                  (TMA engine, mbarrier complete_tx) through a 4-stage ring of 48 KB stages;
+//   k_match_tc     [algo 2] warp 0: one thread streams operand blocks global -> shared with cp.async.bulk
+//                  (TMA engine, mbarrier complete_tx) through a ring of 48 KB stages;
 //                  warp 1: one thread issues tcgen05.mma (M=128, N<=256, K=16, 6 per 32-channel k-block)
 //                  into one of two 256-column TMEM accumulators and commits to mbarriers;
 //                  warps 2-5: epilogue -- tcgen05.ld 16 columns at a time, scale, exp2, running
 //                  sum(e), sum(e*d), max/argmax per set, store one float per (row, set).
 //                  MMA of chunk i+1 overlaps the epilogue of chunk i.
-//                  [algo 3, kFused] warps 6-13 convert the fp32 query tile to bf16 hi/lo inside the kernel instead
-//                  of k_pack_query; correct, but slower at the named shapes (profiles/README.md), so algo 0 = algo 2.
+//   k_match_ts     [algo 3] the query operand never exists in memory as bf16: warp 0 streams the RAW fp32 rows of the
+//                  tile (one 128-byte cp.async.bulk per row and k-block) next to the prototype block; warps 6-9
+//                  (thread = query row = TMEM lane) read their row from shared memory, split it into bf16 hi/lo,
+//                  accumulate the row norm and write the halves with tcgen05.st into a TMEM operand slot; the MMAs
+//                  take A from TMEM and only B from shared memory.  The query is read from HBM once by the whole
+//                  path, k_pack_query and its 2 x 135 MB round trip are gone, and the MMA's shared-memory reads
+//                  drop by a third (ncu: the L1 data pipe, which the MMA operand reads share with every LDG/STS,
+//                  is what limited the earlier LDG -> STS converter variant; see profiles/README.md).
 //
 // Roofline: tensor-bound.  Algorithmic flops per (slice, set) = 2*HW*C*P (executed: 3x that in
 // bf16).  Algorithmic bytes: SURVEY.md section 8(d).
 #include <cstdlib>
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -72,9 +79,19 @@ __host__ __device__ constexpr int smem_bytes(int stages) { return stages * STAGE
 constexpr int MAX_SETS = 128;
 constexpr int MAX_SPLIT = 8;
 constexpr int THREADS = 192;
-constexpr int CONV_WARPS = 8;                    // fused variant: warps 6..13 convert the query tile
-constexpr int THREADS_FUSED = THREADS + CONV_WARPS * 32;
 constexpr int TMEM_COLS = 512;
+// ---- TMEM-sourced fused variant (k_match_ts) ----
+// TMEM budget: 2 accumulators of kNch columns + operand slots of 32 columns (one k-block each: 16 hi + 16 lo) = 512:
+// kNch = 224 -> 2 slots, 208 -> 3, 192 -> 4
+__host__ __device__ constexpr int ts_slots(int nch) { return (TMEM_COLS - 2 * nch) / 32; }
+constexpr int TS_CONV_WARPS = 4;                 // warps 6..9: thread = row of the tile = TMEM lane
+constexpr int TS_THREADS = THREADS + TS_CONV_WARPS * 32;
+constexpr int TS_RAW_PITCH = BK * 4;             // raw fp32 row of a k-block: 128 bytes, 16-byte chunks XOR-swizzled by the TMA unit
+constexpr int TS_RAW_BYTES = BM * TS_RAW_PITCH;  // 16 KB = one tensor-map box (32 channels x 128 rows)
+__host__ __device__ constexpr int ts_b_bytes(int nch) { return nch / 8 * GROUP_BYTES; }          // 28 KB at 224 columns
+__host__ __device__ constexpr int ts_stage_bytes(int nch) { return ts_b_bytes(nch) + TS_RAW_BYTES; }
+__host__ __device__ constexpr int ts_smem_bytes(int stages, int nch) { return stages * ts_stage_bytes(nch) + 1024; }
+static_assert(BK == 32, "k_match_ts is written for 32-channel k-blocks");
 constexpr float LOG2E = 1.4426950408889634f;
 
 __host__ __device__ __forceinline__ int pad16(int x) { return (x + 15) & ~15; }
@@ -121,6 +138,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// one box of a 2-D tensor map (coordinates: channel, row) global -> shared; out-of-range rows / channels arrive as zeros
+__device__ __forceinline__ void tensor_g2s(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -140,6 +166,29 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// the same with A read from TMEM (lane = row, 32-bit column = two consecutive bf16 of the K axis)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 
@@ -302,56 +351,143 @@ __device__ __forceinline__ void fold16(const float (&v)[16], int nvalid, int nba
     }
 }
 
-// kFused = false: both operands arrive as pre-packed images through the TMA engine (k_pack_query ran before).
-// kFused = true : 8 extra "converter" warps read the fp32 query rows of the tile straight from global memory,
-//                 split them into bf16 hi/lo, store them swizzled into the A stage (generic proxy ->
-//                 fence.proxy.async -> mbarrier), and accumulate the row norms on the way: the query is read from
-//                 HBM exactly once by the whole path and no operand image of it is ever written.
+// Column schedule of the persistent CTAs, derived on the device from the prototype counts (no host synchronisation):
+// column splits at set boundaries, as even as the set sizes allow.
+struct Schedule {
+    int count[MAX_SETS];
+    int split_set[MAX_SPLIT + 1], split_col[MAX_SPLIT + 1];
+};
+
+__device__ __forceinline__ void make_schedule(const TcParams& p, Schedule& sch)
+{
+    int T = 0;
+    for (int s = 0; s < p.nsets; ++s) {
+        const int c = p.counts[s];
+        sch.count[s] = c;
+        T += pad16(c);
+    }
+    sch.split_set[0] = 0;
+    sch.split_col[0] = 0;
+    int acc = 0, k = 1;
+    for (int s = 0; s < p.nsets && k < p.nsplit; ++s) {
+        acc += pad16(sch.count[s]);
+        while (k < p.nsplit && (long long)acc * p.nsplit >= (long long)k * T) {
+            sch.split_set[k] = s + 1;
+            sch.split_col[k] = acc;
+            ++k;
+        }
+    }
+    for (; k < p.nsplit; ++k) { sch.split_set[k] = p.nsets; sch.split_col[k] = T; }
+    sch.split_set[p.nsplit] = p.nsets;
+    sch.split_col[p.nsplit] = T;
+}
+
+// Epilogue of both GEMM kernels (warps 2-5): TMEM accumulator chunks of kNch columns -> per-set reductions -> global.
+// kScaleFromSmem: the row scales 20/max(|q|,1e-4) come from the converter warps of the same CTA (k_match_ts) instead of
+// the scale[] array k_pack_query wrote.
+template <int kNch, bool kScaleFromSmem>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule& sch, uint32_t tmem_base, int warp, int lane,
+                                              uint64_t* s_tfull, uint64_t* s_tempty, uint64_t* s_scale_full,
+                                              const float (*s_scale)[BM])
+{
+    const int nitems = p.ntiles * p.nsplit;
+    const int lg = warp & 3;                       // TMEM lane group this warp may read
+    const int row_in_tile = lg * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    uint32_t cit = 0, nz = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const int tile = it / p.nsplit, split = it - tile * p.nsplit;
+        const int c0 = sch.split_col[split];
+        const int g = tile * BM + row_in_tile;
+        const bool valid = g < p.R;
+        const int q = valid ? g / p.HW : 0, pix = valid ? g - q * p.HW : 0;
+        float sc;
+        if (kScaleFromSmem) {
+            sc = 0.f;
+            if (c0 < sch.split_col[split + 1]) {     // the converters publish the row scales of every non-empty item
+                mbar_wait(&s_scale_full[nz & 1], (nz >> 1) & 1);
+                sc = s_scale[nz & 1][row_in_tile];
+                ++nz;
+            }
+        } else {
+            sc = valid ? __ldg(p.scale + g) : 0.f;
+        }
+        const float sc2 = sc * LOG2E;
+        int col = 0;                                // column cursor relative to c0
+        int cur_chunk = -1;
+        uint32_t b = 0;
+        for (int set = sch.split_set[split]; set < sch.split_set[split + 1]; ++set) {
+            const int cnt = sch.count[set];
+            const size_t o = ((size_t)q * p.nsets + set) * p.HW + pix;
+            if (cnt <= 0) {   // empty grid set: the reference raises (alpmodule.py:68); report, write NaN
+                if (valid) {
+                    p.scores[o] = CUDART_NAN_F;
+                    if (p.assign) p.assign[o] = CUDART_NAN_F;
+                }
+                if (g == 0) atomicOr(p.status + set, PSAM_SET_EMPTY);
+                continue;
+            }
+            RowAcc a{0.f, 0.f, -CUDART_INF_F, 0};
+            for (int nb = 0; nb < cnt; nb += 16, col += 16) {
+                const int chunk = col / kNch;
+                if (chunk != cur_chunk) {
+                    if (cur_chunk >= 0) {           // done with the previous accumulator buffer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s_tempty[b]);
+                        ++cit;
+                    }
+                    b = cit & 1;
+                    mbar_wait(&s_tfull[b], (cit >> 1) & 1);
+                    tc_fence_after();
+                    cur_chunk = chunk;
+                }
+                float v[16];
+                tc_ld16(lane_addr + b * kNch + (col - chunk * kNch), v);
+                const int nvalid = cnt - nb;
+                if (nvalid >= 16) fold16<true>(v, 16, nb, sc, sc2, a);
+                else fold16<false>(v, nvalid, nb, sc, sc2, a);
+            }
+            if (valid) {
+                if (p.eff_modes[set] == PSAM_MODE_MASK) {
+                    const float d = a.best * sc;
+                    p.scores[o] = d;
+                    if (p.assign) p.assign[o] = d;
+                } else {
+                    p.scores[o] = a.sed / a.se;
+                    if (p.assign) p.assign[o] = (float)a.bi;
+                }
+            }
+        }
+        if (cur_chunk >= 0) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_tempty[b]);
+            ++cit;
+        }
+    }
+}
+
+// ---- algo 2: both operands arrive as pre-packed images through the TMA engine (k_pack_query ran before) ----
 // STAGES operand stages of 48 KB: 4 fill the SM's shared memory (fastest GEMM when it runs alone); 3 leave ~80 KB, which
 // is what the ALU-bound prompt kernels of ANOTHER volume (k_blocks_warp, k_components) need to be resident on the same SM
 // while the tensor pipe works -- the step is then max(tensor, ALU) instead of their sum.
-template <bool kFused, int STAGES>
-__global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_tc(const TcParams p)
+template <int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2], s_scale_full[2];
-    __shared__ float s_scale[2][BM];
+    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ int s_count[MAX_SETS];
-    __shared__ int s_split_set[MAX_SPLIT + 1], s_split_col[MAX_SPLIT + 1];
+    __shared__ Schedule sch;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     TraceRec* tr = threadIdx.x == 0 ? trace_begin(1) : nullptr;
 
     if (threadIdx.x == 0) {
-        int T = 0;
-        for (int s = 0; s < p.nsets; ++s) {
-            const int c = p.counts[s];
-            s_count[s] = c;
-            T += pad16(c);
-        }
-        // column splits at set boundaries, as even as the set sizes allow
-        s_split_set[0] = 0;
-        s_split_col[0] = 0;
-        int acc = 0, k = 1;
-        for (int s = 0; s < p.nsets && k < p.nsplit; ++s) {
-            acc += pad16(s_count[s]);
-            while (k < p.nsplit && (long long)acc * p.nsplit >= (long long)k * T) {
-                s_split_set[k] = s + 1;
-                s_split_col[k] = acc;
-                ++k;
-            }
-        }
-        for (; k < p.nsplit; ++k) { s_split_set[k] = p.nsets; s_split_col[k] = T; }
-        s_split_set[p.nsplit] = p.nsets;
-        s_split_col[p.nsplit] = T;
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], kFused ? 1 + CONV_WARPS : 1); mbar_init(&s_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_tfull[i], 1);
-            mbar_init(&s_tempty[i], 4);
-            mbar_init(&s_scale_full[i], CONV_WARPS);
-        }
+        make_schedule(p, sch);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_tfull[i], 1); mbar_init(&s_tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -375,7 +511,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
             uint32_t kit = 0;
             for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
                 const int tile = it / p.nsplit, split = it - tile * p.nsplit;
-                const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
+                const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
                 const uint8_t* a_tile = p.a_img + (size_t)tile * p.KB * A_STAGE_BYTES;
                 for (int n0 = c0; n0 < c1; n0 += NCH) {
                     const uint32_t bytes_b = (uint32_t)min(NCH, c1 - n0) * (GROUP_BYTES / 8);
@@ -383,8 +519,8 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                         mbar_wait(&s_empty[s], ph ^ 1);
                         uint8_t* sa = smem + s * STAGE_BYTES;
-                        mbar_expect_tx(&s_full[s], (kFused ? 0 : A_STAGE_BYTES) + bytes_b);
-                        if (!kFused) bulk_g2s(sa, a_tile + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &s_full[s]);
+                        mbar_expect_tx(&s_full[s], A_STAGE_BYTES + bytes_b);
+                        bulk_g2s(sa, a_tile + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &s_full[s]);
                         bulk_g2s(sa + A_STAGE_BYTES, p.b_img + ((size_t)kb * p.G + (n0 >> 3)) * GROUP_BYTES, bytes_b,
                                  &s_full[s]);
                     }
@@ -397,7 +533,7 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
             uint32_t kit = 0, cit = 0;
             for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
                 const int split = it % p.nsplit;
-                const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
+                const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
                 for (int n0 = c0; n0 < c1; n0 += NCH, ++cit) {
                     const uint32_t b = cit & 1, tph = (cit >> 1) & 1;
                     mbar_wait(&s_tempty[b], tph ^ 1);
@@ -423,162 +559,176 @@ __global__ void __launch_bounds__(kFused ? THREADS_FUSED : THREADS, 1) k_match_t
                 }
             }
         }
-    } else if (warp < 6) {
-        // ===== epilogue: TMEM -> per-set reductions -> global =====
-        const int lg = warp & 3;                       // TMEM lane group this warp may read
-        const int row_in_tile = lg * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-        uint32_t cit = 0, nz = 0;
-        for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-            const int tile = it / p.nsplit, split = it - tile * p.nsplit;
-            const int c0 = s_split_col[split];
-            const int g = tile * BM + row_in_tile;
-            const bool valid = g < p.R;
-            const int q = valid ? g / p.HW : 0, pix = valid ? g - q * p.HW : 0;
-            float sc;
-            if (kFused) {
-                sc = 0.f;
-                if (c0 < s_split_col[split + 1]) {     // the converters publish the row scales of every non-empty item
-                    mbar_wait(&s_scale_full[nz & 1], (nz >> 1) & 1);
-                    sc = s_scale[nz & 1][row_in_tile];
-                    ++nz;
-                }
-            } else {
-                sc = valid ? __ldg(p.scale + g) : 0.f;
-            }
-            const float sc2 = sc * LOG2E;
-            int col = 0;                                // column cursor relative to c0
-            int cur_chunk = -1;
-            uint32_t b = 0;
-            for (int set = s_split_set[split]; set < s_split_set[split + 1]; ++set) {
-                const int cnt = s_count[set];
-                const size_t o = ((size_t)q * p.nsets + set) * p.HW + pix;
-                if (cnt <= 0) {   // empty grid set: the reference raises (alpmodule.py:68); report, write NaN
-                    if (valid) {
-                        p.scores[o] = CUDART_NAN_F;
-                        if (p.assign) p.assign[o] = CUDART_NAN_F;
-                    }
-                    if (g == 0) atomicOr(p.status + set, PSAM_SET_EMPTY);
-                    continue;
-                }
-                RowAcc a{0.f, 0.f, -CUDART_INF_F, 0};
-                for (int nb = 0; nb < cnt; nb += 16, col += 16) {
-                    const int chunk = col / NCH;
-                    if (chunk != cur_chunk) {
-                        if (cur_chunk >= 0) {           // done with the previous accumulator buffer
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&s_tempty[b]);
-                            ++cit;
-                        }
-                        b = cit & 1;
-                        mbar_wait(&s_tfull[b], (cit >> 1) & 1);
-                        tc_fence_after();
-                        cur_chunk = chunk;
-                    }
-                    float v[16];
-                    tc_ld16(lane_addr + b * NCH + (col - chunk * NCH), v);
-                    const int nvalid = cnt - nb;
-                    if (nvalid >= 16) fold16<true>(v, 16, nb, sc, sc2, a);
-                    else fold16<false>(v, nvalid, nb, sc, sc2, a);
-                }
-                if (valid) {
-                    if (p.eff_modes[set] == PSAM_MODE_MASK) {
-                        const float d = a.best * sc;
-                        p.scores[o] = d;
-                        if (p.assign) p.assign[o] = d;
-                    } else {
-                        p.scores[o] = a.sed / a.se;
-                        if (p.assign) p.assign[o] = (float)a.bi;
-                    }
-                }
-            }
-            if (cur_chunk >= 0) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_tempty[b]);
-                ++cit;
-            }
-        }
+    } else {
+        epilogue_loop<NCH, false>(p, sch, tmem_base, warp, lane, s_tfull, s_tempty, nullptr, nullptr);
     }
 
-    else if (kFused) {
-        // ===== converters: fp32 query rows -> bf16 hi/lo operand tile in shared memory =====
-        // lane (r = lane & 7, cq = lane >> 3) of converter warp cw owns rows cw*8 + r and 64 + cw*8 + r of the tile
-        // and the 8-channel chunks cq and cq + 4 of every 64-channel k-block: a warp reads 8 rows x 128 contiguous
-        // bytes per load instruction and writes conflict-free 16-byte chunks at their swizzled positions.
-        const int cw = warp - 6, r = lane & 7, cq = lane >> 3;
+    tc_fence_before();
+    __syncthreads();
+    trace_end(tr);
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- algo 3: the fp32 -> bf16 hi/lo split of the query happens inside the GEMM, the A operand lives in TMEM ----
+// Stage s of the ring = [prototype block, TS_NCH columns, swizzled bf16 hi/lo | RAW fp32 rows of the query tile, one
+// 32-channel k-block, as the TMA unit delivers a [32 channels x 128 rows] box of the 2-D tensor map over the query matrix
+// with the 128-byte swizzle].  (One cp.async.bulk per ROW was measured first: 128 small copies per k-block cost ~33 ns
+// each and made the kernel 8x slower; the tensor map needs dense slices, slice_stride == HW * row_stride.)  Per k-block:
+//   warp 0 (1 thread)  waits empty[s]; one cp.async.bulk for the prototype block + one cp.async.bulk.tensor for the
+//                      query box, both counted in bytes on full[s];
+//   warps 6-9          thread = row: wait full[s], 8 x LDS.128 of its row (conflict-free thanks to the swizzle), row
+//                      norm, bf16 hi/lo split in registers, wait a_empty[t], tcgen05.st of 16 hi + 16 lo columns into
+//                      TMEM operand slot t, tcgen05.wait::st, arrive a_full[t];
+//   warp 1 (1 thread)  wait full[s] + a_full[t]; 6 MMAs (hi*hi, lo*hi, hi*lo for both 16-deep halves) with A from
+//                      TMEM and B from shared memory; commit -> empty[s], commit -> a_empty[t];
+//   warps 2-5          epilogue as in k_match_tc, on 224-column accumulators, scales from the converters.
+template <int STAGES, int TS_NCH>
+__global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, const __grid_constant__ CUtensorMap qmap)
+{
+    constexpr int TS_A_SLOTS = ts_slots(TS_NCH), TS_A_COL0 = 2 * TS_NCH;
+    constexpr int TS_B_BYTES = ts_b_bytes(TS_NCH), TS_STAGE_BYTES = ts_stage_bytes(TS_NCH);
+    static_assert(TS_NCH % 16 == 0 && TS_A_SLOTS >= 2 && TS_STAGE_BYTES % 1024 == 0, "stage / TMEM layout");
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2], s_scale_full[2];
+    __shared__ uint64_t s_afull[TS_A_SLOTS], s_aempty[TS_A_SLOTS];
+    __shared__ float s_scale[2][BM];
+    __shared__ uint32_t s_tmem;
+    __shared__ Schedule sch;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    TraceRec* tr = threadIdx.x == 0 ? trace_begin(1) : nullptr;
+
+    if (threadIdx.x == 0) {
+        make_schedule(p, sch);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_tfull[i], 1);
+            mbar_init(&s_tempty[i], 4);
+            mbar_init(&s_scale_full[i], TS_CONV_WARPS);
+        }
+        for (int i = 0; i < TS_A_SLOTS; ++i) { mbar_init(&s_afull[i], TS_CONV_WARPS); mbar_init(&s_aempty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int nitems = p.ntiles * p.nsplit;
+
+    if (warp == 0) {
+        // ===== producer: prototype block + raw query rows, global -> shared =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&qmap) : "memory");
+            uint32_t kit = 0;
+            for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+                const int tile = it / p.nsplit, split = it - tile * p.nsplit;
+                const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
+                for (int n0 = c0; n0 < c1; n0 += TS_NCH) {
+                    const uint32_t bytes_b = (uint32_t)min(TS_NCH, c1 - n0) * (GROUP_BYTES / 8);
+                    for (int kb = 0; kb < p.KB; ++kb, ++kit) {
+                        const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                        mbar_wait(&s_empty[s], ph ^ 1);
+                        uint8_t* sb = smem + s * TS_STAGE_BYTES;
+                        mbar_expect_tx(&s_full[s], bytes_b + TS_RAW_BYTES);      // a box always delivers all its bytes
+                        tensor_g2s(sb + TS_B_BYTES, &qmap, kb * BK, tile * BM, &s_full[s]);
+                        bulk_g2s(sb, p.b_img + ((size_t)kb * p.G + (n0 >> 3)) * GROUP_BYTES, bytes_b, &s_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t kit = 0, cit = 0;
+            for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+                const int split = it % p.nsplit;
+                const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
+                for (int n0 = c0; n0 < c1; n0 += TS_NCH, ++cit) {
+                    const uint32_t b = cit & 1, tph = (cit >> 1) & 1;
+                    mbar_wait(&s_tempty[b], tph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + b * TS_NCH;
+                    const uint32_t idesc = make_idesc(min(TS_NCH, c1 - n0));
+                    for (int kb = 0; kb < p.KB; ++kb, ++kit) {
+                        const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                        const uint32_t t = kit % TS_A_SLOTS, aph = (kit / TS_A_SLOTS) & 1;
+                        mbar_wait(&s_full[s], ph);
+                        mbar_wait(&s_afull[t], aph);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(smem + s * TS_STAGE_BYTES);
+                        const uint32_t a_tmem = tmem_base + TS_A_COL0 + t * 32;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint32_t a_hi = a_tmem + k * 8, a_lo = a_tmem + 16 + k * 8;
+                            const uint64_t b_hi = make_sdesc(b_addr + k * 32), b_lo = make_sdesc(b_addr + PLANE_BYTES + k * 32);
+                            tc_mma_ts(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);
+                            tc_mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                            tc_mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
+                        tc_commit(&s_empty[s]);        // frees the smem stage ...
+                        tc_commit(&s_aempty[t]);       // ... and the TMEM operand slot when these MMAs retire
+                    }
+                    tc_commit(&s_tfull[b]);            // accumulator complete
+                }
+            }
+        }
+    } else if (warp < 6) {
+        epilogue_loop<TS_NCH, true>(p, sch, tmem_base, warp, lane, s_tfull, s_tempty, s_scale_full, s_scale);
+    } else {
+        // ===== converters: raw fp32 row (shared memory) -> bf16 hi/lo -> TMEM operand slot =====
+        const int lg = warp & 3, row = lg * 32 + lane;               // a warp may only touch its own TMEM lane quarter
+        const uint32_t a_lane = tmem_base + ((uint32_t)(lg * 32) << 16) + TS_A_COL0;
         uint32_t kit = 0, nz = 0;
         for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
             const int tile = it / p.nsplit, split = it - tile * p.nsplit;
-            const int c0 = s_split_col[split], c1 = s_split_col[split + 1];
+            const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
             if (c0 >= c1) continue;
-            const float* src[2];
-            bool ok[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int g = tile * BM + j * 64 + cw * 8 + r;
-                ok[j] = g < p.R;
-                const int q = ok[j] ? g / p.HW : 0, pix = ok[j] ? g - q * p.HW : 0;
-                src[j] = p.qry + (size_t)q * p.slice_stride + (size_t)pix * p.row_stride;
-            }
-            float ssq[2] = {0.f, 0.f};
-            float4 cur[8], nxt[8];
-            auto gload = [&](float4 (&v)[8], int kb) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h >= CHUNKS / 4) continue;             // 64-byte rows: one chunk per row and thread
-                        const int k0 = kb * BK + (cq + 4 * h) * 8;
-                        const bool in = ok[j] && k0 < p.C;
-                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[j * 4 + h * 2 + 0] = in ? __ldg(reinterpret_cast<const float4*>(src[j] + k0)) : z;
-                        v[j * 4 + h * 2 + 1] = in ? __ldg(reinterpret_cast<const float4*>(src[j] + k0 + 4)) : z;
-                    }
-            };
-            gload(cur, 0);
-            for (int n0 = c0; n0 < c1; n0 += NCH) {
-                const bool first = (n0 == c0);
+            const bool valid = tile * BM + row < p.R;
+            const int nchunks = (c1 - c0 + TS_NCH - 1) / TS_NCH;
+            float ssq = 0.f;
+            for (int ch = 0; ch < nchunks; ++ch) {
                 for (int kb = 0; kb < p.KB; ++kb, ++kit) {
-                    const bool more = (kb + 1 < p.KB) || (n0 + NCH < c1);
-                    if (more) gload(nxt, kb + 1 < p.KB ? kb + 1 : 0);      // next k-block in flight while this one converts
                     const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                    mbar_wait(&s_empty[s], ph ^ 1);
-                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    const uint32_t t = kit % TS_A_SLOTS, aph = (kit / TS_A_SLOTS) & 1;
+                    mbar_wait(&s_full[s], ph);
+                    // rows beyond R and channels beyond C arrive as zeros; chunk c of row r sits at chunk c ^ (r & 7)
+                    const float4* raw = reinterpret_cast<const float4*>(smem + s * TS_STAGE_BYTES + TS_B_BYTES + row * TS_RAW_PITCH);
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int h = 0; h < CHUNKS / 4; ++h) {
-                            const float4 x = cur[j * 4 + h * 2], y = cur[j * 4 + h * 2 + 1];
-                            const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-                            if (first) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) ssq[j] = fmaf(v[i], v[i], ssq[j]);
-                            }
-                            uint4 hi, lo;
-                            split8(v, hi, lo);
-                            uint8_t* dst = sa + (j * 8 + cw) * GROUP_BYTES + r * ROW_BYTES + (swz(r, cq + 4 * h) << 4);
-                            *reinterpret_cast<uint4*>(dst) = hi;
-                            *reinterpret_cast<uint4*>(dst + PLANE_BYTES) = lo;
-                        }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 x = raw[c ^ (row & 7)];
+                        if (ch == 0) ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ssq))));
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+                        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(x.x - f0.x, x.y - f0.y);
+                        const __nv_bfloat162 l1 = __floats2bfloat162_rn(x.z - f1.x, x.w - f1.y);
+                        hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h0);
+                        hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                        lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l0);
+                        lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+                    }
+                    mbar_wait(&s_aempty[t], aph ^ 1);
+                    tc_fence_after();
+                    tc_st16(a_lane + t * 32, hi);
+                    tc_st16(a_lane + t * 32 + 16, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_full[s]);
-                    if (more) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-                    }
+                    if (lane == 0) mbar_arrive(&s_afull[t]);
                 }
-                if (first) {
-                    // row norms: the 4 lanes with equal r hold the partial sums of one row
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        float t = ssq[j];
-                        t += __shfl_xor_sync(0xffffffffu, t, 8);
-                        t += __shfl_xor_sync(0xffffffffu, t, 16);
-                        if (cq == 0) s_scale[nz & 1][j * 64 + cw * 8 + r] = ok[j] ? 20.0f / fmaxf(sqrtf(t), 1e-4f) : 0.f;
-                    }
+                if (ch == 0) {
+                    s_scale[nz & 1][row] = valid ? 20.0f / fmaxf(sqrtf(ssq), 1e-4f) : 0.f;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_scale_full[nz & 1]);
                     ++nz;
@@ -635,6 +785,11 @@ bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want
     return !want_sims && C % 8 == 0 && nsets <= tc::MAX_SETS && (long long)Q * HW < (1ll << 30);
 }
 
+bool match_ts_supported(const MatchParams& p)
+{
+    return p.Q == 1 || p.slice_stride == (int64_t)p.HW * p.row_stride;
+}
+
 size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fused)
 {
     const tc::Layout L = tc::make_layout(Q, HW, C, nsets, cap_rows);
@@ -642,31 +797,68 @@ size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fu
     return align_up(L.a_bytes, 1024) + align_up(L.b_bytes, 1024) + align_up(L.scale_bytes, 1024) + 1024;
 }
 
-template <bool kFused, int kStages>
-static int launch_gemm(const tc::TcParams& t, int grid, cudaStream_t stream)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
 {
-    using namespace tc;
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [R rows x C channels] fp32, row pitch row_stride floats, boxes of 32 channels x 128 rows, 128-byte swizzle
+static int make_query_map(const MatchParams& p, int R, CUtensorMap* map)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        set_error("psam_alp_match: cuTensorMapEncodeTiled is not available from this driver");
+        return PSAM_ERR_UNSUPPORTED;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)p.C, (cuuint64_t)R};
+    const cuuint64_t gstride[1] = {(cuuint64_t)p.row_stride * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.qry), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("psam_alp_match: cuTensorMapEncodeTiled failed (%d) for C=%d R=%d row_stride=%lld", (int)r, p.C, R,
+                  (long long)p.row_stride);
+        return PSAM_ERR_LAUNCH;
+    }
+    return PSAM_OK;
+}
+
+template <typename K, typename... Extra>
+static int launch_gemm(K kernel, const char* name, int threads, int smem, const tc::TcParams& t, int grid, cudaStream_t stream,
+                       bool* attr_set, const Extra&... extra)
+{
     int dev = 0;
     cudaGetDevice(&dev);
-    static bool attr_set[64] = {};
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {       // once per device
-        cudaError_t e = cudaFuncSetAttribute(k_match_tc<kFused, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             smem_bytes(kStages));
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
-            set_error("k_match_tc: cudaFuncSetAttribute(%d bytes): %s", smem_bytes(kStages), cudaGetErrorString(e));
+            set_error("%s: cudaFuncSetAttribute(%d bytes): %s", name, smem, cudaGetErrorString(e));
             return PSAM_ERR_LAUNCH;
         }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     PSAM_PROF_BEGIN(stream);
-    PSAM_MAX_CARVEOUT((k_match_tc<kFused, kStages>));
-    k_match_tc<kFused, kStages><<<grid, kFused ? THREADS_FUSED : THREADS, smem_bytes(kStages), stream>>>(t);
-    PSAM_CHECK_LAUNCH(kFused ? "k_match_tc_fused" : "k_match_tc");
+    kernel<<<grid, threads, smem, stream>>>(t, extra...);
+    PSAM_CHECK_LAUNCH(name);
     return PSAM_OK;
 }
 
-// operand stages of the packed-image GEMM: 3 by default (co-residency, see k_match_tc); PSAM_TC_STAGES=4 is the
-// experiment knob for the stand-alone optimum
+// operand stages of the GEMMs: 3 by default (co-residency, see k_match_tc); PSAM_TC_STAGES=4 is the experiment knob for
+// the stand-alone optimum
 static int gemm_stages()
 {
     using tc::MAX_STAGES;
@@ -686,6 +878,11 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     using namespace tc;
     if (!match_tc_supported(p.Q, p.HW, p.C, p.nsets, p.cap_rows, p.sims != nullptr)) {
         set_error("psam_alp_match: the tensor-core variant needs C %% 8 == 0, nsets <= %d and sims == NULL", MAX_SETS);
+        return PSAM_ERR_UNSUPPORTED;
+    }
+    if (fused && !match_ts_supported(p)) {
+        set_error("psam_alp_match: algo 3 reads the query through a 2-D tensor map and needs dense slices "
+                  "(slice_stride == HW * row_stride)");
         return PSAM_ERR_UNSUPPORTED;
     }
     const size_t need = match_tc_workspace(p.Q, p.HW, p.C, p.nsets, p.cap_rows, fused);
@@ -721,9 +918,40 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     TcParams t{a_img, b_img, scale, p.counts, p.eff_modes, p.scores, p.assign, p.status,
                p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit, p.qry, p.slice_stride, p.row_stride, p.C};
     const int grid = min(sms, L.ntiles * nsplit);
-    if (fused) return launch_gemm<true, MAX_STAGES>(t, grid, stream);
-    if (MAX_STAGES >= 4 && gemm_stages() == 3) return launch_gemm<false, (MAX_STAGES >= 4 ? 3 : MAX_STAGES)>(t, grid, stream);
-    return launch_gemm<false, MAX_STAGES>(t, grid, stream);
+    constexpr int S3 = MAX_STAGES >= 4 ? 3 : MAX_STAGES;
+    const bool three = MAX_STAGES >= 4 && gemm_stages() == 3;
+    static bool set_tc3[64] = {}, set_tc4[64] = {};
+    if (fused) {
+        CUtensorMap qmap;
+        if (int rc = make_query_map(p, L.R, &qmap)) return rc;
+        // 4 stages of 44 KB by default: unlike the packed kernel, a stage's cycle includes the conversion, and the fourth
+        // stage is worth 12 % to the kernel and 4 % to the pipelined step (measured); PSAM_TS_STAGES / PSAM_TS_NCH are
+        // experiment knobs
+        static int st = 0, nch = 0;
+        if (st == 0) {
+            st = 4; nch = 224;
+            if (const char* ov = getenv("PSAM_TS_STAGES")) st = atoi(ov);
+            if (const char* ov = getenv("PSAM_TS_NCH")) nch = atoi(ov);
+        }
+#define PSAM_TS_CASE(ST, NC)                                                                                      \
+    if (st == ST && nch == NC) {                                                                                  \
+        static bool done[64] = {};                                                                                \
+        PSAM_MAX_CARVEOUT((k_match_ts<ST, NC>));                                                                  \
+        return launch_gemm(k_match_ts<ST, NC>, "k_match_ts", TS_THREADS, ts_smem_bytes(ST, NC), t, grid, stream, done, qmap); \
+    }
+        PSAM_TS_CASE(3, 224) PSAM_TS_CASE(5, 224)
+        PSAM_TS_CASE(3, 208) PSAM_TS_CASE(4, 208) PSAM_TS_CASE(5, 208)
+        PSAM_TS_CASE(3, 192) PSAM_TS_CASE(4, 192) PSAM_TS_CASE(5, 192)
+        st = 4; nch = 224;
+        PSAM_TS_CASE(4, 224)
+#undef PSAM_TS_CASE
+    }
+    if (three) {
+        PSAM_MAX_CARVEOUT(k_match_tc<S3>);
+        return launch_gemm(k_match_tc<S3>, "k_match_tc", THREADS, smem_bytes(S3), t, grid, stream, set_tc3);
+    }
+    PSAM_MAX_CARVEOUT(k_match_tc<MAX_STAGES>);
+    return launch_gemm(k_match_tc<MAX_STAGES>, "k_match_tc", THREADS, smem_bytes(MAX_STAGES), t, grid, stream, set_tc4);
 }
 
 }  // namespace psam

@@ -671,7 +671,7 @@ def test_graphed_volume_step_replays_equal_eager_run(split):
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         gs = GraphedVolumeStep(eng, sup, fg, qry, split_streams=split)
-        assert gs.n_kernels == 2 + 3 + 4            # kernel 1 (2 launches), pack x2 + GEMM, classify + blocks + components + compaction
+        assert gs.n_kernels == 2 + 2 + 4            # kernel 1 (2 launches), prototype pack + fused GEMM, classify + blocks + components + compaction
         h1, r1 = gs.launch()
         gs.join()
         h1, r1 = h1.clone(), r1.clone()
