@@ -43,6 +43,7 @@
 // Roofline: tensor-bound.  Algorithmic flops per (slice, set) = 2*HW*C*P (executed: 3x that in
 // bf16).  Algorithmic bytes: SURVEY.md section 8(d).
 #include <cstdlib>
+#include <type_traits>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -126,6 +127,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
+        : "memory");
+}
+
+// The same for waiters with slack (producer, converters, epilogue): the try_wait carries a suspend-time hint, so the warp
+// sleeps in hardware until the phase completes instead of re-issuing the try (ncu: 30 % of the instructions the fused
+// kernel executed were YIELD/TRYWAIT/BRA spins, issue slots the co-resident prompt kernels of other volumes want).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(1000000u)
         : "memory");
 }
 
@@ -228,6 +247,17 @@ __device__ __forceinline__ float ex2(float x)
 }
 
 // ------------------------------------------------------------------------------ operand packing
+// 2 fp32 -> packed bf16 hi pair + packed bf16 lo pair, three instructions per element: one F2FP for the hi pair, a shift /
+// mask to read the two halves back as fp32, one subtraction each, one F2FP for the lo pair
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo)
+{
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&hb);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&lb);
+}
+
 // 8 fp32 -> 8 bf16 hi + 8 bf16 lo (x = hi + lo up to 2^-17 relative)
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo)
 {
@@ -336,19 +366,36 @@ struct RowAcc {
     int bi;
 };
 
-template <bool kFull>
-__device__ __forceinline__ void fold16(const float (&v)[16], int nvalid, int nbase, float sc, float sc2, RowAcc& a)
+// One 16-column group of a row folded into the running reductions of its set.
+//   kGrid : softmax-weighted sum: se += e, sed += e*x with e = exp(20*cos - 20) (x is the raw dot product; the row scale
+//           is applied to sed once per set)
+//   kMax  : running maximum ('mask' mode, and the argmax of `assign`); kIndex additionally tracks its column
+template <bool kFull, bool kGrid, bool kMax, bool kIndex>
+__device__ __forceinline__ void fold16(const float (&v)[16], int nvalid, int nbase, float sc2, RowAcc& a)
 {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         if (kFull || j < nvalid) {
             const float x = v[j];
-            const float e = ex2(fmaf(x, sc2, -20.0f * LOG2E));   // exp(d - 20), d = x*sc in [-20, 20]
-            a.se += e;
-            a.sed = fmaf(e, x * sc, a.sed);
-            if (x > a.best) { a.best = x; a.bi = nbase + j; }
+            if (kGrid) {
+                const float e = ex2(fmaf(x, sc2, -20.0f * LOG2E));   // exp(d - 20), d = x*sc in [-20, 20]
+                a.se += e;
+                a.sed = fmaf(e, x, a.sed);
+            }
+            if (kIndex) {
+                if (x > a.best) { a.best = x; a.bi = nbase + j; }
+            } else if (kMax) {
+                a.best = fmaxf(a.best, x);
+            }
         }
     }
+}
+
+template <bool kGrid, bool kMax, bool kIndex>
+__device__ __forceinline__ void fold16_any(const float (&v)[16], int nvalid, int nbase, float sc2, RowAcc& a)
+{
+    if (nvalid >= 16) fold16<true, kGrid, kMax, kIndex>(v, 16, nbase, sc2, a);
+    else fold16<false, kGrid, kMax, kIndex>(v, nvalid, nbase, sc2, a);
 }
 
 // Column schedule of the persistent CTAs, derived on the device from the prototype counts (no host synchronisation):
@@ -394,6 +441,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule&
     const int lg = warp & 3;                       // TMEM lane group this warp may read
     const int row_in_tile = lg * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    const bool want_index = p.assign != nullptr;
     uint32_t cit = 0, nz = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
         const int tile = it / p.nsplit, split = it - tile * p.nsplit;
@@ -405,7 +453,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule&
         if (kScaleFromSmem) {
             sc = 0.f;
             if (c0 < sch.split_col[split + 1]) {     // the converters publish the row scales of every non-empty item
-                mbar_wait(&s_scale_full[nz & 1], (nz >> 1) & 1);
+                mbar_wait_relaxed(&s_scale_full[nz & 1], (nz >> 1) & 1);
                 sc = s_scale[nz & 1][row_in_tile];
                 ++nz;
             }
@@ -428,6 +476,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule&
                 continue;
             }
             RowAcc a{0.f, 0.f, -CUDART_INF_F, 0};
+            const bool is_mask = p.eff_modes[set] == PSAM_MODE_MASK;
             for (int nb = 0; nb < cnt; nb += 16, col += 16) {
                 const int chunk = col / kNch;
                 if (chunk != cur_chunk) {
@@ -438,23 +487,25 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule&
                         ++cit;
                     }
                     b = cit & 1;
-                    mbar_wait(&s_tfull[b], (cit >> 1) & 1);
+                    mbar_wait_relaxed(&s_tfull[b], (cit >> 1) & 1);
                     tc_fence_after();
                     cur_chunk = chunk;
                 }
                 float v[16];
                 tc_ld16(lane_addr + b * kNch + (col - chunk * kNch), v);
                 const int nvalid = cnt - nb;
-                if (nvalid >= 16) fold16<true>(v, 16, nb, sc, sc2, a);
-                else fold16<false>(v, nvalid, nb, sc, sc2, a);
+                // the engine path asks for no `assign`: grid sets then need no maximum at all, 'mask' sets no exponential
+                if (is_mask) fold16_any<false, true, false>(v, nvalid, nb, sc2, a);
+                else if (want_index) fold16_any<true, true, true>(v, nvalid, nb, sc2, a);
+                else fold16_any<true, false, false>(v, nvalid, nb, sc2, a);
             }
             if (valid) {
-                if (p.eff_modes[set] == PSAM_MODE_MASK) {
+                if (is_mask) {
                     const float d = a.best * sc;
                     p.scores[o] = d;
                     if (p.assign) p.assign[o] = d;
                 } else {
-                    p.scores[o] = a.sed / a.se;
+                    p.scores[o] = a.sed * sc / a.se;
                     if (p.assign) p.assign[o] = (float)a.bi;
                 }
             }
@@ -517,7 +568,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
                     const uint32_t bytes_b = (uint32_t)min(NCH, c1 - n0) * (GROUP_BYTES / 8);
                     for (int kb = 0; kb < p.KB; ++kb, ++kit) {
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                        mbar_wait(&s_empty[s], ph ^ 1);
+                        mbar_wait_relaxed(&s_empty[s], ph ^ 1);
                         uint8_t* sa = smem + s * STAGE_BYTES;
                         mbar_expect_tx(&s_full[s], A_STAGE_BYTES + bytes_b);
                         bulk_g2s(sa, a_tile + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &s_full[s]);
@@ -638,7 +689,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
                     const uint32_t bytes_b = (uint32_t)min(TS_NCH, c1 - n0) * (GROUP_BYTES / 8);
                     for (int kb = 0; kb < p.KB; ++kb, ++kit) {
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                        mbar_wait(&s_empty[s], ph ^ 1);
+                        mbar_wait_relaxed(&s_empty[s], ph ^ 1);
                         uint8_t* sb = smem + s * TS_STAGE_BYTES;
                         mbar_expect_tx(&s_full[s], bytes_b + TS_RAW_BYTES);      // a box always delivers all its bytes
                         tensor_g2s(sb + TS_B_BYTES, &qmap, kb * BK, tile * BM, &s_full[s]);
@@ -697,43 +748,38 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
             const bool valid = tile * BM + row < p.R;
             const int nchunks = (c1 - c0 + TS_NCH - 1) / TS_NCH;
             float ssq = 0.f;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                for (int kb = 0; kb < p.KB; ++kb, ++kit) {
-                    const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                    const uint32_t t = kit % TS_A_SLOTS, aph = (kit / TS_A_SLOTS) & 1;
-                    mbar_wait(&s_full[s], ph);
-                    // rows beyond R and channels beyond C arrive as zeros; chunk c of row r sits at chunk c ^ (r & 7)
-                    const float4* raw = reinterpret_cast<const float4*>(smem + s * TS_STAGE_BYTES + TS_B_BYTES + row * TS_RAW_PITCH);
-                    uint32_t hi[16], lo[16];
+            // one k-block: this thread's row of the box -> 16 hi + 16 lo packed columns in TMEM operand slot t
+            auto convert = [&](auto first_chunk) {
+                constexpr bool kNorm = decltype(first_chunk)::value;
+                const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                const uint32_t t = kit % TS_A_SLOTS, aph = (kit / TS_A_SLOTS) & 1;
+                ++kit;
+                mbar_wait_relaxed(&s_full[s], ph);
+                // rows beyond R and channels beyond C arrive as zeros; chunk c of row r sits at chunk c ^ (r & 7)
+                const float4* raw = reinterpret_cast<const float4*>(smem + s * TS_STAGE_BYTES + TS_B_BYTES + row * TS_RAW_PITCH);
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 x = raw[c ^ (row & 7)];
-                        if (ch == 0) ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ssq))));
-                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-                        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(x.x - f0.x, x.y - f0.y);
-                        const __nv_bfloat162 l1 = __floats2bfloat162_rn(x.z - f1.x, x.w - f1.y);
-                        hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h0);
-                        hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h1);
-                        lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l0);
-                        lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l1);
-                    }
-                    mbar_wait(&s_aempty[t], aph ^ 1);
-                    tc_fence_after();
-                    tc_st16(a_lane + t * 32, hi);
-                    tc_st16(a_lane + t * 32 + 16, lo);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_afull[t]);
+                for (int c = 0; c < 8; ++c) {
+                    const float4 x = raw[c ^ (row & 7)];
+                    if (kNorm) ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ssq))));
+                    split2(x.x, x.y, hi[2 * c], lo[2 * c]);
+                    split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
                 }
-                if (ch == 0) {
-                    s_scale[nz & 1][row] = valid ? 20.0f / fmaxf(sqrtf(ssq), 1e-4f) : 0.f;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_scale_full[nz & 1]);
-                    ++nz;
-                }
-            }
+                mbar_wait_relaxed(&s_aempty[t], aph ^ 1);
+                tc_fence_after();
+                tc_st16(a_lane + t * 32, hi);
+                tc_st16(a_lane + t * 32 + 16, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_afull[t]);
+            };
+            for (int kb = 0; kb < p.KB; ++kb) convert(std::true_type{});
+            s_scale[nz & 1][row] = valid ? 20.0f / fmaxf(sqrtf(ssq), 1e-4f) : 0.f;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_scale_full[nz & 1]);
+            ++nz;
+            for (int rest = (nchunks - 1) * p.KB; rest > 0; --rest) convert(std::false_type{});
         }
     }
 
