@@ -473,6 +473,10 @@ def gpu_arm(args, cfg):
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_channels))   # small messages: few CTAs suffice
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    # N > 1: the persistent GEMM grid leaves a few SMs to short-lived CTAs, so that the NCCL kernels of the volumes in
+    # flight do not wait for a GEMM CTA to retire (psam_match_reserve_sms; 2 GPUs: 0.346 -> 0.328 ms per volume with 8)
+    reserve = args.reserve_sms if args.reserve_sms >= 0 else (8 if world > 1 else 0)
+    _lib.match_reserve_sms(reserve)
 
     Q, L, C, h, w = cfg["Q"], cfg["L"], cfg["C"], cfg["h"], cfg["w"]
     NL = max(1, args.lanes)
@@ -764,6 +768,8 @@ def main():
                     help="cap NCCL channels (0 = NCCL's default): the collectives move a few MB, and every extra channel "
                          "is a CTA that competes with the compute kernels for SMs (4 measured best at 2 GPUs in round 2: "
                          "0.382 ms/step vs 0.406 with 2 and 0.390 with 8)")
+    ap.add_argument("--reserve-sms", type=int, default=-1,
+                    help="SMs the persistent match kernel leaves free (psam_match_reserve_sms); -1 = 8 when N > 1, else 0")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from Python instead of CUDA graphs")
     ap.add_argument("--lanes", type=int, default=4, help="volumes in flight per GPU (CUDA streams)")
     ap.add_argument("--graph-collectives", type=int, default=0,

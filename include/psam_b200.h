@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PSAM_ABI_VERSION 2
+#define PSAM_ABI_VERSION 3
 
 typedef void* psam_stream_t; /* cudaStream_t */
 
@@ -150,6 +150,14 @@ int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, int vw, floa
  *              operand images, 3 = the same GEMM with the fp32 -> bf16 hi/lo conversion of the query fused into it.
  * ------------------------------------------------------------------------------------ */
 size_t psam_alp_match_workspace(int Q, int HW, int C, int nsets, int cap_rows, int algo);
+
+/* The tensor-core match kernels are persistent: one CTA per SM for the whole launch.  psam_match_reserve_sms(n) makes them
+ * leave n SMs without such a CTA (process-wide; n < 0 only queries; returns the previous value; default 0, or
+ * PSAM_TC_RESERVE_SMS).  For multi-GPU runs with several volumes in flight: the NCCL kernels of the other volumes'
+ * prototype broadcast / record gather (no counterpart in the single-GPU reference) then find an
+ * SM whose CTAs are all short-lived instead of waiting for a GEMM CTA to retire (2 GPUs, config 2: 0.346 -> 0.328 ms per
+ * volume with n = 8). */
+int psam_match_reserve_sms(int n);
 
 int psam_alp_match(const float* qry, int64_t slice_stride, int64_t row_stride, int Q, int HW, int C,
                    const float* protos, int cap_rows, const int32_t* counts, const int32_t* eff_modes,

@@ -18,7 +18,7 @@ MODE_IDS = {"mask": MODE_MASK, "gridconv": MODE_GRIDCONV, "gridconv+": MODE_GRID
 MODE_NAMES = {v: k for k, v in MODE_IDS.items()}
 
 SET_EMPTY = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 PROB_SOFTMAX, PROB_SOFTMAX_TWICE = 0, 1
 IMG_EMPTY, IMG_RUN_OVERFLOW, IMG_CC_TRUNCATED, IMG_CCA_AMBIGUOUS = 1, 2, 4, 8
 REC_SELECTED = 1
@@ -48,6 +48,7 @@ SIGNATURES = {
     "psam_mask_nearest": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "psam_alp_proto_grid": (c_i, [c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
     "psam_alp_match_workspace": (c_sz, [c_i] * 6),
+    "psam_match_reserve_sms": (c_i, [c_i]),
     "psam_alp_match": (c_i, [c_p, c_i64, c_i64, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p,
                              c_p, c_sz, c_i, c_p]),
     "psam_upsample_workspace": (c_sz, [c_i, c_i]),
@@ -91,6 +92,12 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().psam_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def match_reserve_sms(n: int = -1) -> int:
+    """SMs the persistent match kernels leave free (multi-GPU runs: room for the NCCL kernels of other volumes in
+    flight); n < 0 only queries.  Returns the previous value."""
+    return int(load().psam_match_reserve_sms(int(n)))
 
 
 def launch_count() -> int:

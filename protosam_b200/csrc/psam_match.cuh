@@ -28,6 +28,7 @@ bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want
 // fused = the GEMM converts the fp32 query rows itself (no packed query image, no separate pass over the query)
 // the fused variant additionally needs dense slices (one 2-D tensor map over all query rows)
 bool match_ts_supported(const MatchParams& p);
+int match_reserve_sms(int n);
 size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fused);
 int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, bool fused, cudaStream_t stream);
 

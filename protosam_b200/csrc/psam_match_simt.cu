@@ -211,6 +211,8 @@ extern "C" size_t psam_alp_match_workspace(int Q, int HW, int C, int nsets, int 
     return match_tc_workspace(Q, HW, C, nsets, cap_rows, algo == 3);
 }
 
+extern "C" int psam_match_reserve_sms(int n) { return match_reserve_sms(n); }
+
 extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t row_stride, int Q, int HW, int C,
                               const float* protos, int cap_rows, const int32_t* counts, const int32_t* eff_modes,
                               int nsets, float* scores, float* assign, float* sims, int32_t* status, void* workspace,

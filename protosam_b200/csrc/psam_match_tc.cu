@@ -42,6 +42,8 @@
 //
 // Roofline: tensor-bound.  Algorithmic flops per (slice, set) = 2*HW*C*P (executed: 3x that in
 // bf16).  Algorithmic bytes: SURVEY.md section 8(d).
+#include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -209,6 +211,13 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+}
+
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
 }
 
 // 16 consecutive fp32 columns of this thread's TMEM lane
@@ -757,18 +766,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
                 mbar_wait_relaxed(&s_full[s], ph);
                 // rows beyond R and channels beyond C arrive as zeros; chunk c of row r sits at chunk c ^ (r & 7)
                 const float4* raw = reinterpret_cast<const float4*>(smem + s * TS_STAGE_BYTES + TS_B_BYTES + row * TS_RAW_PITCH);
-                uint32_t hi[16], lo[16];
+                // two halves of 16 channels: 8 hi + 8 lo columns each (TMEM slot: hi columns 0-15, lo columns 16-31), so
+                // that at most 16 packed values + 16 raw floats are live
+                float4 x[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 x = raw[c ^ (row & 7)];
-                    if (kNorm) ssq = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ssq))));
-                    split2(x.x, x.y, hi[2 * c], lo[2 * c]);
-                    split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
-                }
+                for (int c = 0; c < 4; ++c) x[c] = raw[c ^ (row & 7)];
                 mbar_wait_relaxed(&s_aempty[t], aph ^ 1);
                 tc_fence_after();
-                tc_st16(a_lane + t * 32, hi);
-                tc_st16(a_lane + t * 32 + 16, lo);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (kNorm) ssq = fmaf(x[c].x, x[c].x, fmaf(x[c].y, x[c].y, fmaf(x[c].z, x[c].z, fmaf(x[c].w, x[c].w, ssq))));
+                        split2(x[c].x, x[c].y, hi[2 * c], lo[2 * c]);
+                        split2(x[c].z, x[c].w, hi[2 * c + 1], lo[2 * c + 1]);
+                    }
+                    if (half == 0) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) x[c] = raw[(4 + c) ^ (row & 7)];
+                    }
+                    tc_st8(a_lane + t * 32 + half * 8, hi);
+                    tc_st8(a_lane + t * 32 + 16 + half * 8, lo);
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -823,6 +843,20 @@ static Layout make_layout(int Q, int HW, int C, int nsets, int cap_rows)
 }
 
 }  // namespace tc
+
+// SMs the persistent GEMM grids leave free (psam_match_reserve_sms); n < 0 queries
+int match_reserve_sms(int n)
+{
+    static std::atomic<int> v{-1};
+    int cur = v.load(std::memory_order_relaxed);
+    if (cur < 0) {
+        cur = 0;
+        if (const char* ov = getenv("PSAM_TC_RESERVE_SMS")) cur = std::max(0, atoi(ov));
+        v.store(cur, std::memory_order_relaxed);
+    }
+    if (n >= 0) v.store(n, std::memory_order_relaxed);
+    return cur;
+}
 
 PSAM_TRACE_TU();
 bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want_sims)
@@ -963,7 +997,15 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     }
     TcParams t{a_img, b_img, scale, p.counts, p.eff_modes, p.scores, p.assign, p.status,
                p.nsets, p.HW, L.R, L.ntiles, L.KB, L.G, nsplit, p.qry, p.slice_stride, p.row_stride, p.C};
-    const int grid = min(sms, L.ntiles * nsplit);
+    // Grid: the items are equal-sized, so a launch takes ceil(items / CTAs) rounds whatever the CTA count inside a round
+    // bracket; take the FEWEST CTAs that keep the round count (config 2: 686 items = 5 rounds on 138..148 CTAs -> 138).
+    // The SMs left over carry only short-lived CTAs: room for the prompt kernels and the NCCL kernels of the other
+    // volumes in flight at no cost to the GEMM.  psam_match_reserve_sms() additionally caps the CTA count.
+    const int reserve = max(0, min(match_reserve_sms(-1), sms - 1));
+    const int nitems = L.ntiles * nsplit, cap = min(sms - reserve, nitems);
+    const int rounds = (nitems + cap - 1) / cap;
+    int grid = (nitems + rounds - 1) / rounds;
+    if (getenv("PSAM_TC_FULL_GRID")) grid = cap;          // experiment knob
     constexpr int S3 = MAX_STAGES >= 4 ? 3 : MAX_STAGES;
     const bool three = MAX_STAGES >= 4 && gemm_stages() == 3;
     static bool set_tc3[64] = {}, set_tc4[64] = {};

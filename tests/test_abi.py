@@ -46,7 +46,7 @@ def test_ctypes_table_covers_header(lib):
 
 def test_abi_version_and_struct_layout(lib):
     from protosam_b200 import ops
-    assert lib.psam_abi_version() == 2
+    assert lib.psam_abi_version() == 3
     assert ops.REC_DTYPE.itemsize == 96 and ops.HDR_DTYPE.itemsize == 64
     assert ops.REC_DTYPE.fields["centroid"][1] == 48 and ops.REC_DTYPE.fields["conf"][1] == 64
     assert ops.HDR_DTYPE.fields["bg_centroid"][1] == 40
