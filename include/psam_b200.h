@@ -311,6 +311,19 @@ int psam_neg_points(const int32_t* labels, const float* p_bg, int64_t p_bg_image
                     const psam_prompt_rec* recs, int n_img, int out, int max_cc, int use_cca, int ring_width, float thresh,
                     int host_aliasing, psam_neg_point* neg /* [n_img, max_cc + 1] */, psam_stream_t stream);
 
+/* get_most_conf_points(output_p_fg, pred, k) for any k (models/ProtoSAM.py:266-289; production uses k = 1, which the
+ * records already carry): for component r of image i, pts[i][r][j] = (x, y) and conf[i][r][j] = p_fg of the j-th entry of
+ * torch.topk(p_fg[component], k) -- ATen's CPU algorithm (partial_sort for k * 64 <= area, nth_element + sort below)
+ * replayed, so equal probabilities come out in the reference's order.  Components with fewer than k pixels (torch.topk
+ * raises) and slots beyond n_rec get pts = -1.  k <= 64.
+ *   p_fg   foreground probabilities at every pixel, image i at p_fg + i * p_fg_image_stride (= channel 1 of probs2) */
+size_t psam_topk_points_workspace(int n_img, int max_cc, int k);
+
+int psam_topk_points(const int32_t* labels, const float* p_fg, int64_t p_fg_image_stride, const psam_image_hdr* hdr,
+                     const psam_prompt_rec* recs, int n_img, int out, int max_cc, int use_cca, int k,
+                     int64_t* pts /* [n_img,max_cc,k,2] */, float* conf /* [n_img,max_cc,k] */,
+                     void* workspace, size_t workspace_bytes, psam_stream_t stream);
+
 /* get_sam_input_mask + the mask_input of predict_w_masks (models/ProtoSAM.py:452-476): per component the 0/1 mask
  * resized to size x size (cv2.INTER_NEAREST), foreground 10, background -8 cast to uint8 (= 248).  Masks are packed in
  * image order: masks[offsets[i] + r] belongs to component r of image i; offsets [n_img + 1] is written here; masks

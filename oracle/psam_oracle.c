@@ -583,6 +583,153 @@ int psamo_topk1_pos(const float* vals, int n)
     return q[0].i;
 }
 
+/* torch.topk(v, k) (largest, sorted) on a 1-D CPU tensor for any k, restated from the same ATen loop
+ * (get_most_conf_points with k > 1, models/ProtoSAM.py:266-289):
+ *   k * 64 <= n -> std::partial_sort(begin, begin + k, end, greater)  = __heap_select + __sort_heap
+ *   else        -> std::nth_element(begin, begin + k - 1, end, greater) then std::sort(begin, begin + k - 1, greater)
+ * libstdc++'s algorithms replayed move for move (only values are compared, so the order of equal values is whatever
+ * these algorithms leave).  Writes the k positions in torch's output order; returns 0, or -1 if k > n. */
+static void tk_push_heap(tk_t* first, long hole, long top, tk_t value)
+{
+    long parent = (hole - 1) / 2;
+    while (hole > top && TK_GT(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+static void tk_adjust_heap(tk_t* first, long hole, long len, tk_t value)
+{
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (TK_GT(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    tk_push_heap(first, hole, top, value);
+}
+
+static void tk_make_heap(tk_t* first, tk_t* last)
+{
+    const long len = last - first;
+    if (len < 2) return;
+    long parent = (len - 2) / 2;
+    for (;;) {
+        tk_t value = first[parent];
+        tk_adjust_heap(first, parent, len, value);
+        if (parent == 0) return;
+        parent--;
+    }
+}
+
+static void tk_pop_heap(tk_t* first, tk_t* last, tk_t* result)
+{
+    tk_t value = *result;
+    *result = *first;
+    tk_adjust_heap(first, 0, last - first, value);
+}
+
+static void tk_heap_select(tk_t* first, tk_t* middle, tk_t* last)
+{
+    tk_make_heap(first, middle);
+    for (tk_t* i = middle; i < last; ++i)
+        if (TK_GT(*i, *first)) tk_pop_heap(first, middle, i);
+}
+
+static void tk_sort_heap(tk_t* first, tk_t* last)
+{
+    while (last - first > 1) {
+        --last;
+        tk_pop_heap(first, last, last);
+    }
+}
+
+static tk_t* tk_partition_pivot(tk_t* first, tk_t* last)
+{
+    tk_t* mid = first + (last - first) / 2;
+    tk_move_median_to_first(first, first + 1, mid, last - 1);
+    return tk_unguarded_partition(first + 1, last, first);
+}
+
+static int tk_lg(long n) { int d = 0; for (; n > 1; n >>= 1) ++d; return d; }
+
+static void tk_introselect(tk_t* first, tk_t* nth, tk_t* last, int depth)
+{
+    while (last - first > 3) {
+        if (depth == 0) {
+            tk_heap_select(first, nth + 1, last);
+            tk_swap(first, nth);
+            return;
+        }
+        --depth;
+        tk_t* cut = tk_partition_pivot(first, last);
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    tk_insertion_sort(first, last);
+}
+
+static void tk_introsort_loop(tk_t* first, tk_t* last, int depth)
+{
+    while (last - first > 16) {
+        if (depth == 0) {
+            tk_heap_select(first, last, last);
+            tk_sort_heap(first, last);
+            return;
+        }
+        --depth;
+        tk_t* cut = tk_partition_pivot(first, last);
+        tk_introsort_loop(cut, last, depth);
+        last = cut;
+    }
+}
+
+static void tk_unguarded_linear_insert(tk_t* last)
+{
+    tk_t val = *last;
+    tk_t* next = last - 1;
+    while (TK_GT(val, *next)) { *last = *next; last = next; --next; }
+    *last = val;
+}
+
+static void tk_sort(tk_t* first, tk_t* last)
+{
+    if (first == last) return;
+    tk_introsort_loop(first, last, tk_lg(last - first) * 2);
+    if (last - first > 16) {
+        tk_insertion_sort(first, first + 16);
+        for (tk_t* i = first + 16; i != last; ++i) tk_unguarded_linear_insert(i);
+    } else {
+        tk_insertion_sort(first, last);
+    }
+}
+
+int psamo_topk_pos(const float* vals, int n, int k, int32_t* out_pos)
+{
+    if (k < 1 || k > n) return -1;
+    tk_t* q = (tk_t*)malloc((size_t)n * sizeof(tk_t));
+    for (int i = 0; i < n; ++i) { q[i].v = vals[i]; q[i].i = i; }
+    if ((long)k * 64 <= n) {
+        tk_heap_select(q, q + k, q + n);
+        tk_sort_heap(q, q + k);
+    } else {
+        tk_t* nth = q + k - 1;
+        if (nth != q + n) tk_introselect(q, nth, q + n, tk_lg(n) * 2);
+        tk_sort(q, q + k - 1);
+    }
+    for (int i = 0; i < k; ++i) out_pos[i] = q[i].i;
+    free(q);
+    return 0;
+}
+
 /* For every label j in 1..nlab-1: bbox [min_x,min_y,max_x,max_y] (inclusive,
  * get_bbox_per_cc :242-264) and the most confident pixel (x,y) =
  * torch.nonzero(mask)[torch.topk(p_fg[mask], 1).indices] (get_most_conf_points

@@ -239,6 +239,92 @@ __global__ void __launch_bounds__(NT) k_confidence(const float* __restrict__ p_f
 
 using namespace psam;
 
+// get_most_conf_points for any k: one thread per component replays torch.topk over the component's pixels in raster order
+// (they are read through the component's box).  Selection work for a rarely used variant: correctness, not speed.
+__global__ void __launch_bounds__(32) k_topk_points(const int32_t* __restrict__ labels, const float* __restrict__ p_fg,
+                                                    int64_t p_stride, const psam_image_hdr* __restrict__ hdr,
+                                                    const psam_prompt_rec* __restrict__ recs, int n_img, int out, int max_cc,
+                                                    int use_cca, int k, int64_t* __restrict__ pts, float* __restrict__ conf,
+                                                    TK* __restrict__ scratch)
+{
+    const int slot = blockIdx.x * 32 + threadIdx.x;
+    if (slot >= n_img * max_cc) return;
+    const int img = slot / max_cc, r = slot - img * max_cc;
+    int64_t* o_pts = pts + (size_t)slot * k * 2;
+    float* o_conf = conf + (size_t)slot * k;
+    for (int j = 0; j < k; ++j) { o_pts[2 * j] = -1; o_pts[2 * j + 1] = -1; o_conf[j] = 0.f; }
+    if (r >= hdr[img].n_rec) return;
+    const psam_prompt_rec rec = recs[slot];
+    const int n = rec.area;
+    if (n < k) return;                                   // torch.topk raises: the host wrapper does
+    const int want = use_cca ? 1 : rec.label;
+    const int32_t* lab = labels + (size_t)img * out * out;
+    const float* pf = p_fg + (size_t)img * p_stride;
+    const int x0 = (int)rec.box[0], y0 = (int)rec.box[1], x1 = (int)rec.box[2], y1 = (int)rec.box[3];
+    TK heap[TOPK_MAX_K];
+    TK* q;
+    if ((long long)k * 64 <= n) {
+        // partial_sort: heap of the first k pixels, every later pixel replaces the top only if strictly larger
+        q = heap;
+        int c = 0;
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                const int idx = y * out + x;
+                if (lab[idx] != want) continue;
+                TK e{pf[idx], idx};
+                if (c < k) {
+                    q[c] = e;
+                    if (++c == k) tk_make_heap(q, k);
+                } else if (tk_gt(e, q[0])) {
+                    tk_adjust_heap(q, 0, k, e);          // __pop_heap: the old top leaves the range
+                }
+            }
+        tk_sort_heap(q, k);
+    } else {
+        // n < 64 k: nth_element + sort over all pixels of the component, staged in this slot's scratch
+        q = scratch + (size_t)slot * 64 * k;
+        int c = 0;
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                const int idx = y * out + x;
+                if (lab[idx] == want) q[c++] = TK{pf[idx], idx};
+            }
+        tk_introselect(q, 0, k - 1, n);
+        tk_sort(q, k - 1);
+    }
+    for (int j = 0; j < k; ++j) {
+        o_pts[2 * j] = q[j].i % out;
+        o_pts[2 * j + 1] = q[j].i / out;
+        o_conf[j] = q[j].v;
+    }
+}
+
+extern "C" size_t psam_topk_points_workspace(int n_img, int max_cc, int k)
+{
+    if (n_img < 1 || max_cc < 1 || k < 1) return 256;
+    return align_up((size_t)n_img * max_cc * 64 * k * sizeof(TK), 256);
+}
+
+extern "C" int psam_topk_points(const int32_t* labels, const float* p_fg, int64_t p_fg_image_stride, const psam_image_hdr* hdr,
+                                const psam_prompt_rec* recs, int n_img, int out, int max_cc, int use_cca, int k, int64_t* pts,
+                                float* conf, void* workspace, size_t workspace_bytes, psam_stream_t stream_)
+{
+    PSAM_TRACE("psam_topk_points");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSAM_CHECK_ARG(labels && p_fg && hdr && recs && pts && conf, "psam_topk_points: null pointer");
+    PSAM_CHECK_ARG(n_img >= 1 && out >= 1 && max_cc >= 1 && (long long)n_img * max_cc < (1ll << 30), "psam_topk_points: bad shape");
+    PSAM_CHECK_ARG(k >= 1 && k <= TOPK_MAX_K, "psam_topk_points: k = %d not in [1, %d]", k, TOPK_MAX_K);
+    if (!workspace || workspace_bytes < psam_topk_points_workspace(n_img, max_cc, k)) {
+        set_error("psam_topk_points: workspace too small (%zu < %zu)", workspace_bytes, psam_topk_points_workspace(n_img, max_cc, k));
+        return PSAM_ERR_WORKSPACE;
+    }
+    PSAM_PROF_BEGIN(stream);
+    k_topk_points<<<(n_img * max_cc + 31) / 32, 32, 0, stream>>>(labels, p_fg, p_fg_image_stride, hdr, recs, n_img, out, max_cc,
+                                                               use_cca ? 1 : 0, k, pts, conf, static_cast<TK*>(workspace));
+    PSAM_CHECK_LAUNCH("k_topk_points");
+    return PSAM_OK;
+}
+
 extern "C" int psam_neg_points(const int32_t* labels, const float* p_bg, int64_t p_bg_image_stride, const psam_image_hdr* hdr,
                                const psam_prompt_rec* recs, int n_img, int out, int max_cc, int use_cca, int ring_width,
                                float thresh, int host_aliasing, psam_neg_point* neg, psam_stream_t stream_)

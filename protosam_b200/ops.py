@@ -337,6 +337,23 @@ def neg_points(labels, p_bg, hdr, recs, use_cca=False, ring_width=10, thresh=0.9
     return neg
 
 
+def topk_points(labels, p_fg, hdr, recs, k, use_cca=False):
+    """get_most_conf_points for any k (models/ProtoSAM.py:266-289): -> (pts int64 [n,max_cc,k,2] in (x, y), conf float32
+    [n,max_cc,k]), torch.topk's order within each component; -1 where a component has fewer than k pixels."""
+    L = _lib.load()
+    _need_cuda(p_fg)
+    n, out, _ = labels.shape
+    max_cc = recs.shape[1]
+    assert p_fg.stride(2) == 1 and p_fg.stride(1) == out and labels.is_contiguous()
+    pts = torch.empty((n, max_cc, k, 2), dtype=torch.int64, device=labels.device)
+    conf = torch.empty((n, max_cc, k), dtype=torch.float32, device=labels.device)
+    ws = _ws(L.psam_topk_points_workspace(n, max_cc, int(k)), labels.device)
+    rc = L.psam_topk_points(_ptr(labels), _ptr(p_fg), p_fg.stride(0), _ptr(hdr.contiguous()), _ptr(recs.contiguous()), n, out,
+                            max_cc, int(bool(use_cca)), int(k), _ptr(pts), _ptr(conf), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "psam_topk_points")
+    return pts, conf
+
+
 def mask_prompts(labels, hdr, recs, use_cca=False, size=256, capacity=None):
     """Mask prompts (models/ProtoSAM.py:452-476): -> (masks uint8 [capacity,size,size] with 10 / 248, offsets int32 [n+1]);
     component r of image i is masks[offsets[i] + r]."""

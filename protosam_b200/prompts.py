@@ -231,17 +231,26 @@ def get_bbox_per_cc(conn_components: ConnectedComponents) -> np.ndarray:
 def get_most_conf_points(conn_components: ConnectedComponents, cc_id: int, k: int = 1):
     """models/ProtoSAM.py:266-289 for one component: ``(locations int64 [k,2] in (x, y), [confidences])``.
     The reference masks the 1024^2 probability map on the host and calls torch.topk; here kernel 3b already found,
-    per component, the highest p_fg with torch.topk's tie rule (first pixel in raster order), so the answer is read
-    off the component's record.  Production uses k = num_points_for_sam = 1 (validation_protosam.py:226); k > 1
-    would need the full map on the host and is rejected rather than approximated."""
-    if k != 1:
-        raise NotImplementedError("only the reference's production setting k = 1 is computed on the device")
+    per component, the highest p_fg with torch.topk's tie rule, so for k = 1 (production: num_points_for_sam = 1,
+    validation_protosam.py:226) the answer is read off the component's record.  k > 1 replays torch.topk on the device
+    over the component's pixels (psam_topk_points), equal probabilities in the reference's order; like torch.topk it
+    raises when the component has fewer than k pixels."""
     recs = conn_components.records
     hit = np.nonzero(recs["label"] == cc_id)[0]
     if len(hit) == 0:
         return None, None
     r = recs[hit[0]]
-    return r["conf_pt"].astype(np.int64)[None, :].copy(), [float(r["conf_pt_p"])]
+    if k == 1:
+        return r["conf_pt"].astype(np.int64)[None, :].copy(), [float(r["conf_pt_p"])]
+    if int(r["area"]) < k:
+        raise RuntimeError(f"selected index k out of range: component {cc_id} has {int(r['area'])} pixels, k = {k}")
+    d = conn_components.dev
+    cache = d.setdefault("topk", {})
+    if k not in cache:                                   # one launch serves every component of the image
+        pts, conf = ops.topk_points(d["labels"], d["probs2"][:, 1], d["hdr"], d["recs"], k, use_cca=d["use_cca"])
+        cache[k] = (pts[0].cpu().numpy(), conf[0].cpu().numpy())
+    pts, conf = cache[k]
+    return pts[hit[0]].copy(), [float(c) for c in conf[hit[0]]]
 
 
 def get_sam_input_points(conn_components: ConnectedComponents, output_p=None, get_neg_points=False, l=1,

@@ -313,6 +313,44 @@ def test_function_level_dropins_match_oracle():
     assert np.array_equal(PR.cca(pred, _t(lg)), O.cca(pred, p[0, 1]))
 
 
+@pytest.mark.parametrize("scale", [9.0, 40.0])
+def test_most_conf_points_any_k_matches_torch_topk(scale):
+    """get_most_conf_points(output_p_fg, pred, k) for k > 1 (models/ProtoSAM.py:266-289): the device replay of torch.topk
+    == torch.topk itself on the reference's masked map, for components on both sides of ATen's k * 64 <= n switch and
+    with saturated (exactly equal) probabilities at scale 40."""
+    import torch as _torch
+    lg = (torch.nn.functional.interpolate(torch.from_numpy(synth.gaussian_like(33, (1, 2, 11, 11)) * scale), size=(384, 384),
+                                          mode="bicubic")).numpy().astype(np.float32)
+    # speckle: many small components (nth_element + sort side) next to the big ones (partial_sort side)
+    rng = np.random.default_rng(3)
+    lg[0, 1] += (rng.random((384, 384)) < 0.02).astype(np.float32) * 2 * scale
+    p = O.softmax2(lg)
+    pred = (p[0, 1] > p[0, 0]).astype(np.uint8)
+    cc, _ = PR.get_connected_components(pred, _t(lg), return_conf=True)
+    rcc, _ = O.get_connected_components(pred, p[0, 1], return_conf=True)
+    assert cc[0] == rcc[0] and cc[0] > 20
+    areas = cc[2][:, 4]
+    pf = _torch.from_numpy(p[0, 1])
+    checked = {"partial_sort": 0, "nth_element": 0, "raises": 0}
+    for k in (2, 3, 5, 17):
+        for j in range(1, cc[0]):
+            if areas[j] < k:
+                with pytest.raises(RuntimeError):
+                    PR.get_most_conf_points(cc, j, k)
+                checked["raises"] += 1
+                continue
+            if areas[j] > 2000 and j % 3:            # keep the runtime down: every third big component
+                continue
+            m = _torch.from_numpy(rcc[1] == j)
+            v, i = _torch.topk(pf[m], k)
+            ref_loc = _torch.nonzero(m)[i][:, [1, 0]].numpy()
+            loc, conf = PR.get_most_conf_points(cc, j, k)
+            assert loc.dtype == ref_loc.dtype and np.array_equal(loc, ref_loc), (k, j, int(areas[j]))
+            assert conf == [float(x) for x in v]
+            checked["partial_sort" if k * 64 <= areas[j] else "nth_element"] += 1
+    assert checked["partial_sort"] > 0 and checked["nth_element"] > 10
+
+
 # ------------------------------------------------------------------------------ whole path
 
 @pytest.mark.parametrize("cfg_name,nq", [("cfg1_vits_256", 1), ("cfg2_chaos_mri", 3), ("cfg3_synapse_ct", 2)])

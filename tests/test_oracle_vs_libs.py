@@ -105,6 +105,31 @@ def test_topk1_tie_behaviour_matches_torch():
             assert got == ref, (n, t, v.tolist())
 
 
+def test_topk_any_k_tie_behaviour_matches_torch():
+    """torch.topk(v, k): partial_sort when k * 64 <= n, nth_element + sort otherwise; with many equal values the order
+    among ties is a function of libstdc++'s algorithms, which the oracle replays (get_most_conf_points, k > 1)."""
+    L = O.lib()
+    L.psamo_topk_pos.restype = ctypes.c_int
+    rng = np.random.default_rng(11)
+    cases = [(n, k) for n in (1, 2, 3, 4, 5, 7, 16, 17, 18, 33, 63, 64, 65, 127, 128, 129, 200, 319, 320, 321, 640, 1000, 5000)
+             for k in (1, 2, 3, 5, 10, 16, 17, 40) if k <= n]
+    for n, k in cases:
+        for t in range(12):
+            levels = int(rng.integers(1, 6))
+            v = (rng.integers(0, levels + 1, n) / levels).astype(np.float32)
+            if t % 4 == 0:
+                v = rng.random(n).astype(np.float32)
+            if t % 4 == 1:                                   # saturated probabilities: mostly exactly 1.0
+                v = np.where(rng.random(n) < 0.8, 1.0, rng.random(n)).astype(np.float32)
+            ref = torch.topk(torch.from_numpy(v), k).indices.numpy()
+            got = np.zeros(k, np.int32)
+            assert L.psamo_topk_pos(v.ctypes.data_as(ctypes.c_void_p), n, k, got.ctypes.data_as(ctypes.c_void_p)) == 0
+            assert np.array_equal(got, ref), (n, k, t)
+    got = np.zeros(4, np.int32)
+    v = np.ones(3, np.float32)
+    assert L.psamo_topk_pos(v.ctypes.data_as(ctypes.c_void_p), 3, 4, got.ctypes.data_as(ctypes.c_void_p)) == -1
+
+
 def test_nearest_resize_matches_torch():
     m = synth.ellipse_mask(5, 518)
     for hw in (37, 32, 48, 73):
