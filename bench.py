@@ -41,7 +41,7 @@ DTYPE = "f32 (contraction: bf16x3 split operands, fp32 accumulate in TMEM; every
 N_ROTATE = 4            # distinct input volumes cycled through the timed region (> L2 in total)
 
 
-def workload_desc(cfg, n_gpus, scaling="weak", q_total=None):
+def workload_desc(cfg, n_gpus, scaling="weak", q_total=None, p2p=False):
     per_gpu = cfg["Q"] if scaling == "weak" else None
     return {
         "workload": (f"{cfg['name']}: 1 support + {cfg['Q']} query slices {'per GPU' if scaling == 'weak' else 'in total'}, "
@@ -53,8 +53,9 @@ def workload_desc(cfg, n_gpus, scaling="weak", q_total=None):
         "l2_policy": f"{N_ROTATE} distinct query volumes rotate through the timed region "
                      f"({N_ROTATE * cfg['Q'] * cfg['h'] * cfg['w'] * cfg['C'] * 4 / 1e6:.0f} MB of inputs + "
                      f"{cfg['Q'] * cfg['L'] * 0.5:.0f} MB of per-step intermediates > 126 MB L2)",
-        "parallelism": f"slices sharded over {n_gpus} GPU(s); prototype broadcast (source rank = lane % ranks) + "
-                       "gather of the compacted records to rank 0",
+        "parallelism": f"slices sharded over {n_gpus} GPU(s); prototype table from the source rank (= lane % ranks) to every "
+                       "rank + the compacted records to rank 0, " +
+                       ("one-sided stores over NVLink peer memory (psam_peer_*)" if p2p else "NCCL broadcast + gather"),
         "lanes": f"{cfg.get('lanes', 1)} volume(s) in flight per GPU on separate CUDA streams",
     }
 
@@ -289,7 +290,8 @@ class Pipeline:
         self.qvols = [base] + [self.rank_volume(k, rank) for k in range(1, n_rotate)]
         self.NL = NL = max(1, args.lanes)
         self.engs = [CoarseVolumeEngine((h, w), cfg["img_size"], out_size=1024, val_wsize=cfg["ws"], use_cca=False,
-                                        point_mode="both", match_algo=args.algo, group=groups[ln]) for ln in range(NL)]
+                                        point_mode="both", match_algo=args.algo, group=groups[ln],
+                                        p2p=bool(getattr(args, "p2p", 0)) and world > 1) for ln in range(NL)]
         self.split = bool(getattr(args, "split_streams", False)) and use_graphs
         # split: the lane's own stream carries the match stage, the prompt stage runs on a second, higher-priority stream
         self.lanes = [torch.cuda.Stream(device=dev) for _ in range(NL)]
@@ -352,8 +354,8 @@ class Pipeline:
             _, _, buf = e.prompts_from_logits(logits, n_alloc=n_alloc, return_packed=True)
             if ev is not None:
                 ev[2].record()
-            self.pending[ln] = gather_packed(buf, self.counts_all, ("compact", n_alloc, n_alloc * e.recs_per_image), dst=0,
-                                             group=self.groups[ln], async_op=True)
+            self.pending[ln] = e.collect_records(buf, self.counts_all, ("compact", n_alloc, n_alloc * e.recs_per_image), dst=0,
+                                                 async_op=True)
             return self.pending[ln]
 
     def drain(self):
@@ -736,7 +738,7 @@ def gpu_arm(args, cfg):
     line = {
         "metric": METRIC, "value": q_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
-        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": workload_desc(cfg, world, scaling, q_total),
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": workload_desc(cfg, world, scaling, q_total, p2p=bool(args.p2p) and world > 1),
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": q_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "records_complete": e2e_ok,
@@ -768,6 +770,9 @@ def main():
                     help="cap NCCL channels (0 = NCCL's default): the collectives move a few MB, and every extra channel "
                          "is a CTA that competes with the compute kernels for SMs (4 measured best at 2 GPUs in round 2: "
                          "0.382 ms/step vs 0.406 with 2 and 0.390 with 8)")
+    ap.add_argument("--p2p", type=int, default=1,
+                    help="N > 1: 1 = prototype table and prompt records move with one-sided stores over NVLink peer memory "
+                         "(psam_peer_*, no collective library on the path); 0 = NCCL broadcast + gather")
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="SMs the persistent match kernel leaves free (psam_match_reserve_sms); -1 = 8 when N > 1, else 0")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue every kernel from Python instead of CUDA graphs")

@@ -285,6 +285,45 @@ int psam_coarse_to_prompts(const float* logits, int n_img, int h, int w, int mid
                            void* workspace, size_t workspace_bytes, psam_stream_t stream);
 
 /* --------------------------------------------------------------------------------------
+ * Multi-GPU exchanges over NVLink peer memory (the reference is single-GPU; north_star shards the
+ * query slices of a volume over the GPUs of one box, sends the support prototypes to every rank and brings the prompt
+ * records back).  One-sided: a sender stores straight into the receiver's memory and raises a signal word there; no
+ * collective library on the path.  The caller provides, per channel, one REGION per rank -- a symmetric allocation that
+ * every peer has mapped (e.g. torch.distributed._symmetric_memory.empty + rendezvous; `regions` is the device array of
+ * the world's region addresses as THIS rank sees them, its `buffer_ptrs_dev`) -- zero-initialised before first use, of
+ * psam_peer_region_bytes(payload) bytes: PSAM_PEER_SIGNAL_BYTES of signal words, then the payload ("mailbox").  `ctr` is
+ * 16 zero-initialised bytes of local device memory: one for a table channel (push and recv share it), two for a record
+ * channel (put, collect); epochs live there, so the calls can be captured into CUDA graphs.  Source and destination
+ * ranks may change from one exchange to the next.  Every rank must issue the matching calls in the same order; a peer that never answers
+ * traps the waiting kernel after 20 s instead of hanging the GPU.
+ *
+ *   psam_peer_push_table  (source rank) waits until every peer acknowledged the previous table, writes the LIVE rows
+ *                         (counts[s] of cap_rows per set) + the integer arrays of its prototype table into every peer's
+ *                         mailbox, signals.  table = the packed buffer of psam_alp_prototypes' outputs: rows at 0, the
+ *                         integer arrays (counts first) at ints_offset.
+ *   psam_peer_recv_table  (other ranks) waits for the signal, copies mailbox -> its private table, acknowledges.
+ *   psam_peer_put         (every rank) waits for dst's acknowledgement of the previous round, writes nbytes into slot
+ *                         `rank` (slot_bytes apart) of dst's mailbox, signals.
+ *   psam_peer_collect     (dst, after its own psam_peer_put on the same stream; put_ctr = that call's ctr) waits for every
+ *                         rank's signal, copies the world slots -> out, acknowledges to all.
+ * ------------------------------------------------------------------------------------ */
+#define PSAM_PEER_SIGNAL_BYTES 4096
+
+size_t psam_peer_region_bytes(size_t payload_bytes);
+
+int psam_peer_push_table(const void* table, int nsets, int cap_rows, int C, size_t ints_offset, size_t ints_bytes,
+                         void* const* regions, int world, int rank, void* ctr, psam_stream_t stream);
+
+int psam_peer_recv_table(void* table, int nsets, int cap_rows, int C, size_t ints_offset, size_t ints_bytes,
+                         void* const* regions, int world, int rank, int src, void* ctr, psam_stream_t stream);
+
+int psam_peer_put(const void* src, size_t nbytes, size_t slot_bytes, void* const* regions, int world, int rank, int dst,
+                  void* ctr, psam_stream_t stream);
+
+int psam_peer_collect(void* out, size_t slot_bytes, void* const* regions, int world, int rank, const void* put_ctr, void* ctr,
+                      psam_stream_t stream);
+
+/* --------------------------------------------------------------------------------------
  * Optional prompt variants of ProtoSAM.forward (off in the reference's configs, config_ssl_upload.py:93,102).  They
  * consume what psam_upsample_softmax (fg_only = 0, probs2) and psam_components (labels_out) leave on the device.
  * ------------------------------------------------------------------------------------ */

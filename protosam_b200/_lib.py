@@ -60,6 +60,11 @@ SIGNATURES = {
     "psam_coarse_to_prompts": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     "psam_packed_bytes": (c_sz, [c_i, c_i]),
     "psam_compact_records": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "psam_peer_region_bytes": (c_sz, [c_sz]),
+    "psam_peer_push_table": (c_i, [c_p, c_i, c_i, c_i, c_sz, c_sz, c_p, c_i, c_i, c_p, c_p]),
+    "psam_peer_recv_table": (c_i, [c_p, c_i, c_i, c_i, c_sz, c_sz, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "psam_peer_put": (c_i, [c_p, c_sz, c_sz, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "psam_peer_collect": (c_i, [c_p, c_sz, c_p, c_i, c_i, c_p, c_p, c_p]),
     "psam_topk_points_workspace": (c_sz, [c_i] * 3),
     "psam_topk_points": (c_i, [c_p, c_p, c_i64, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     "psam_neg_points": (c_i, [c_p, c_p, c_i64, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),

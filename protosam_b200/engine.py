@@ -135,7 +135,7 @@ class CoarseVolumeEngine:
                  proto_grid_size: int = 8, use_cca: bool = False, point_mode: str = "both",
                  max_cc: int = ops.DEFAULT_MAX_CC, max_runs: int = ops.DEFAULT_MAX_RUNS, fg_mode: str = "auto_fg",
                  match_algo: int = 0, group=None, variant: str = "protosam",
-                 recs_per_image: int = ops.DEFAULT_RECS_PER_IMAGE):
+                 recs_per_image: int = ops.DEFAULT_RECS_PER_IMAGE, p2p: bool = False):
         self.h, self.w = int(feature_hw[0]), int(feature_hw[1])
         self.img_size, self.out_size = int(img_size), int(out_size)
         self.val_wsize = int(val_wsize)
@@ -154,12 +154,57 @@ class CoarseVolumeEngine:
         self.protos: Optional[dict] = None
         self.n_labels, self.n_shots = 0, 1
         self._ws = None
+        # p2p (world > 1, CUDA): the prototype table and the prompt records move with one-sided stores over NVLink peer
+        # memory (ops.PeerChannel, psam_peer_*) instead of NCCL collectives; the channels are created on first use
+        # (a collective, blocking step: the first set_support / run_sharded must not be inside a graph capture)
+        self.p2p = bool(p2p)
+        self._channels = {}
 
     # -- distributed helpers -------------------------------------------------------------------
     def _world(self):
         if dist.is_available() and dist.is_initialized():
             return dist.get_world_size(self.group), dist.get_rank(self.group)
         return 1, 0
+
+    def _channel(self, kind: str, payload_bytes: int, device) -> "ops.PeerChannel":
+        ch = self._channels.get(kind)
+        if ch is None or ch.payload_bytes < payload_bytes:
+            ch = ops.PeerChannel(payload_bytes, self.group, device)
+            self._channels[kind] = ch
+        return ch
+
+    def send_table(self, protos: dict, src: int = 0):
+        """The prototype table from `src` to every rank: one-sided pushes of the live rows (p2p) or one NCCL / gloo
+        broadcast of the packed table."""
+        world, rank = self._world()
+        if world == 1:
+            return protos
+        if not self.p2p:
+            return broadcast_prototypes(protos, src=src, group=self.group)
+        ch = self._channel("table", protos["packed"].numel(), protos["packed"].device)
+        if rank == src:
+            ops.peer_push_table(ch, protos)
+        else:
+            ops.peer_recv_table(ch, protos, src)
+        return protos
+
+    def collect_records(self, buf: torch.Tensor, counts: Sequence[int], layout, dst: int = 0, async_op: bool = False):
+        """This rank's packed record buffer to `dst`: one-sided puts into dst's mailbox (p2p; dst copies the slots out and
+        the returned handle reads that copy -- consume it before this engine's next collect_records) or one gather."""
+        if not self.p2p:
+            return gather_packed(buf, counts, layout, dst=dst, group=self.group, async_op=async_op)
+        world, rank = self._world()
+        slot = (buf.numel() + 15) // 16 * 16
+        ch = self._channel("records", slot * world, buf.device)
+        assert ch.payload_bytes // world // 16 * 16 == slot, "collect_records: the record buffer size changed"
+        ops.peer_put(ch, buf, dst)
+        bucket = None
+        if rank == dst:
+            out = torch.empty((world, slot), dtype=torch.uint8, device=buf.device)
+            ops.peer_collect(ch, out)
+            bucket = [o[: buf.numel()] for o in out.unbind(0)]
+        pend = PendingGather(None, bucket, list(counts), layout, buf)
+        return pend if async_op else pend.result()
 
     # -- support side ----------------------------------------------------------------------------
     def set_support(self, sup_feats: torch.Tensor, fg_masks: torch.Tensor, src: int = 0, broadcast: bool = True):
@@ -193,7 +238,7 @@ class CoarseVolumeEngine:
             protos.update(N=N, gh=gh, gw=gw, S=S, C=C)
         self.protos = protos
         if broadcast:
-            broadcast_prototypes(protos, src=src, group=self.group)
+            self.send_table(protos, src=src)
         return self.protos
 
     def set_support_from_image_masks(self, sup_feats: torch.Tensor, fg_img_masks: torch.Tensor, src: int = 0,
@@ -238,8 +283,8 @@ class CoarseVolumeEngine:
             out = self.run(qry_local)
             return PendingGather.done(out) if async_op else out
         _, _, buf = self.prompts_from_logits(self.match(qry_local), n_alloc=max(counts), return_packed=True)
-        return gather_packed(buf, counts, ("compact", max(counts), max(counts) * self.recs_per_image), dst=dst,
-                             group=self.group, async_op=async_op)
+        return self.collect_records(buf, counts, ("compact", max(counts), max(counts) * self.recs_per_image), dst=dst,
+                                    async_op=async_op)
 
     def decode(self, hdr: torch.Tensor, recs: torch.Tensor, on_empty_set: str = "raise") -> List[List[P.SlicePrompts]]:
         """Device records -> per slice, per label prompt objects (one D2H copy).  recs is dense [n,max_cc,96] or compact
@@ -310,24 +355,34 @@ class GraphedVolumeStep:
         q_total = q_total if q_total is not None else qry_local.shape[0] * world
         self.counts = [(hi - lo) * L for lo, hi in (shard_range(q_total, world, r) for r in range(world))]
         n_alloc = max(self.counts)
-        # eager warm-up on the current stream: sizes workspaces, sets kernel attributes, primes the allocator
+        # eager warm-up on the current stream: sizes workspaces, sets kernel attributes, primes the allocator (and, with
+        # the engine's p2p exchanges, creates the peer channels: a collective step that cannot be captured)
+        p2p = bool(getattr(eng, "p2p", False)) and world > 1
+        self.layout = ("compact", n_alloc, n_alloc * eng.recs_per_image)
         eng.set_support(sup_feats, fg_masks, src=src)
-        eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc, return_packed=True)
+        _, _, buf0 = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc, return_packed=True)
+        if p2p:
+            eng.collect_records(buf0, self.counts, self.layout, dst=dst)
         torch.cuda.current_stream().synchronize()
         self.g1 = None
         k0 = ops._lib.launch_count()
-        self.one_graph = self.one_graph and world > 1 and not self.split
+        # p2p: the exchanges are kernels of this library, so a volume is always ONE graph (split_streams does not apply)
+        self.split = self.split and not p2p
+        self.one_graph = (self.one_graph or p2p) and world > 1 and not self.split
+        self._p2p_pending = None
         if self.one_graph:
-            self.layout = ("compact", n_alloc, n_alloc * eng.recs_per_image)
             nb = ops.packed_bytes(n_alloc, n_alloc * eng.recs_per_image)
             self.bucket = (list(torch.empty((world, nb), dtype=torch.uint8, device=qry_local.device).unbind(0))
-                           if rank == dst else None)
+                           if rank == dst and not p2p else None)
             self.gall = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.gall):
-                eng.set_support(sup_feats, fg_masks, src=src)          # kernel 1 on `src` + the broadcast
+                eng.set_support(sup_feats, fg_masks, src=src)          # kernel 1 on `src` + the broadcast / push
                 self.hdr, self.recs, self.buf = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc,
                                                                         return_packed=True)
-                dist.gather(self.buf, self.bucket, dst=dst, group=eng.group)
+                if p2p:
+                    self._p2p_pending = eng.collect_records(self.buf, self.counts, self.layout, dst=dst, async_op=True)
+                else:
+                    dist.gather(self.buf, self.bucket, dst=dst, group=eng.group)
             self.protos = eng.protos
             self.n_kernels = int(ops._lib.launch_count() - k0)
             self.n_alloc = n_alloc
@@ -358,7 +413,6 @@ class GraphedVolumeStep:
             self._prompts_recorded = False
         self.n_kernels = int(ops._lib.launch_count() - k0)      # library kernels one launch() replays
         self.n_alloc = n_alloc
-        self.layout = ("compact", n_alloc, n_alloc * eng.recs_per_image)
         self._pending = None
 
     def launch(self, async_gather: bool = True, gather: bool = True):
@@ -369,6 +423,8 @@ class GraphedVolumeStep:
             if not gather:
                 n = self.counts[self.rank]
                 return self.hdr[:n], self.recs[:n]
+            if self._p2p_pending is not None:
+                return PendingGather(None, self._p2p_pending.bucket, list(self.counts), self.layout, self.buf)
             return PendingGather(None, self.bucket, list(self.counts), self.layout, self.buf)
         if self.split:
             return self._launch_split(async_gather, gather)

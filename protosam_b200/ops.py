@@ -337,6 +337,81 @@ def neg_points(labels, p_bg, hdr, recs, use_cca=False, ring_width=10, thresh=0.9
     return neg
 
 
+# ---------------------------------------------------------------------------------------------
+# One-sided exchanges over NVLink peer memory (include/psam_b200.h, psam_peer_*)
+# ---------------------------------------------------------------------------------------------
+
+class PeerChannel:
+    """One symmetric region per rank ([signal words | mailbox of payload_bytes]) mapped into every peer through
+    torch.distributed._symmetric_memory, plus the local epoch counters of the two directions.  Creating one is a
+    collective, blocking call (allocation + rendezvous + barrier): do it outside CUDA-graph capture."""
+
+    def __init__(self, payload_bytes: int, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        L = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.payload_bytes = int(payload_bytes)
+        nbytes = int(L.psam_peer_region_bytes(self.payload_bytes))
+        self.region = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.region.zero_()
+        self.handle = symm_mem.rendezvous(self.region, self.group)
+        self.regions_dev = int(self.handle.buffer_ptrs_dev)          # device array of the world's region addresses
+        self.ctr = torch.zeros(8, dtype=torch.int32, device=device)  # [send epoch, done, pad, pad | recv epoch, done, pad, pad]
+        torch.cuda.current_stream().synchronize()
+        self.handle.barrier()                                        # nobody signals into a region that is not zeroed yet
+        torch.cuda.current_stream().synchronize()
+
+    def _ctr(self, recv: bool) -> int:
+        return self.ctr.data_ptr() + (16 if recv else 0)
+
+
+def _table_geom(protos):
+    packed, rows = protos["packed"], protos["protos"]
+    nsets, cap, C = rows.shape
+    ints_offset = protos["counts"].data_ptr() - packed.data_ptr()
+    return nsets, cap, C, ints_offset, packed.numel() - ints_offset
+
+
+def peer_push_table(ch: PeerChannel, protos):
+    """source rank: live prototype rows + integer arrays -> every peer's mailbox (waits for their previous acknowledgement)"""
+    L = _lib.load()
+    nsets, cap, C, io, ib = _table_geom(protos)
+    assert protos["packed"].numel() <= ch.payload_bytes
+    rc = L.psam_peer_push_table(_ptr(protos["packed"]), nsets, cap, C, io, ib, ch.regions_dev, ch.world, ch.rank, ch._ctr(False),
+                                _stream())
+    _lib.check(rc, "psam_peer_push_table")
+
+
+def peer_recv_table(ch: PeerChannel, protos, src: int):
+    """other ranks: wait for the source's table, copy it out of the mailbox into `protos`, acknowledge"""
+    L = _lib.load()
+    nsets, cap, C, io, ib = _table_geom(protos)
+    assert protos["packed"].numel() <= ch.payload_bytes
+    rc = L.psam_peer_recv_table(_ptr(protos["packed"]), nsets, cap, C, io, ib, ch.regions_dev, ch.world, ch.rank, int(src),
+                                ch._ctr(False), _stream())
+    _lib.check(rc, "psam_peer_recv_table")
+
+
+def peer_put(ch: PeerChannel, buf, dst: int):
+    """every rank: `buf` (uint8, a multiple of 16 bytes) -> slot `rank` of dst's mailbox"""
+    L = _lib.load()
+    slot = ch.payload_bytes // ch.world // 16 * 16
+    assert buf.is_contiguous() and buf.numel() % 16 == 0 and buf.numel() <= slot
+    rc = L.psam_peer_put(_ptr(buf), buf.numel(), slot, ch.regions_dev, ch.world, ch.rank, int(dst), ch._ctr(False), _stream())
+    _lib.check(rc, "psam_peer_put")
+
+
+def peer_collect(ch: PeerChannel, out):
+    """dst: wait for every rank's slot, copy the mailbox -> out (uint8 [world, slot_bytes]), acknowledge to all"""
+    L = _lib.load()
+    slot = ch.payload_bytes // ch.world // 16 * 16
+    assert out.is_contiguous() and out.shape == (ch.world, slot)
+    rc = L.psam_peer_collect(_ptr(out), slot, ch.regions_dev, ch.world, ch.rank, ch._ctr(False), ch._ctr(True), _stream())
+    _lib.check(rc, "psam_peer_collect")
+
+
 def topk_points(labels, p_fg, hdr, recs, k, use_cca=False):
     """get_most_conf_points for any k (models/ProtoSAM.py:266-289): -> (pts int64 [n,max_cc,k,2] in (x, y), conf float32
     [n,max_cc,k]), torch.topk's order within each component; -1 where a component has fewer than k pixels."""

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q_total, out_q):
+def _worker(rank, world, port, q_total, p2p, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -35,7 +35,7 @@ def _worker(rank, world, port, q_total, out_q):
         sup, fg = torch.from_numpy(vol.sup).to(dev), torch.from_numpy(vol.fg).to(dev)
         lo, hi = shard_range(q_total, world, rank)
         mine = torch.from_numpy(vol.qry[lo:hi]).to(dev)
-        eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"])
+        eng = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"], p2p=p2p)
         if rank != 0:
             sup = torch.zeros_like(sup)              # only the source rank's support features may matter
         eng.set_support(sup, fg, src=0)
@@ -46,6 +46,18 @@ def _worker(rank, world, port, q_total, out_q):
         gs.launch()
         h2, r2 = gs.launch().result()
         torch.cuda.synchronize()
+        # source and destination ranks may change from one exchange to the next (bench.py's lanes use src = lane % ranks)
+        sup1 = torch.from_numpy(vol.sup).to(dev) if rank == 1 else torch.zeros_like(sup)
+        eng.set_support(sup1, fg, src=1)
+        h3, r3 = eng.run_sharded(mine, q_total, dst=1)
+        eng.set_support(sup, fg, src=0)
+        h4, r4 = eng.run_sharded(mine, q_total, dst=0)
+        torch.cuda.synchronize()
+        swapped_ok = (h3 is not None) == (rank == 1) and (h4 is not None) == (rank == 0)
+        if rank == 1:
+            swapped_ok &= h3.shape[0] == q_total * L
+        if rank == 0:
+            swapped_ok &= torch.equal(h4, hdr_all) and torch.equal(r4, recs_all)
         if rank == 0:
             solo = CoarseVolumeEngine((cfg["h"], cfg["w"]), cfg["img_size"], val_wsize=cfg["ws"])
             solo.set_support(sup, fg, broadcast=False)
@@ -63,24 +75,27 @@ def _worker(rank, world, port, q_total, out_q):
             a = solo.decode(hs, rs)
             b = solo.decode(hdr_all, recs_all)
             ok &= all(x.empty == y.empty and (x.empty or np.array_equal(x.points, y.points)) for x, y in zip(sum(a, []), sum(b, [])))
-            out_q.put(bool(ok))
+            out_q.put(bool(ok) and bool(swapped_ok))
         else:
-            out_q.put(hdr_all is None and recs_all is None and h2 is None)
+            out_q.put(hdr_all is None and recs_all is None and h2 is None and bool(swapped_ok))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("q_total", [4, 5])
-def test_sharded_volume_over_nccl_equals_single_rank(q_total):
+def test_sharded_volume_over_nccl_equals_single_rank(q_total, p2p):
+    """p2p: the table and the records move with the library's one-sided peer-memory kernels (psam_peer_*) instead of the
+    NCCL broadcast / gather; the gathered records must be the same bytes either way."""
     ctx = mp.get_context("spawn")
     out_q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q_total, out_q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q_total, p2p, out_q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [out_q.get(timeout=300) for _ in procs]
+    res = [out_q.get(timeout=150) for _ in procs]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
