@@ -150,6 +150,19 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "memory");
 }
 
+// Named barriers for plain shared-memory hand-offs between warp groups (the row scales of k_match_ts): the producers
+// arrive without waiting, the consumers sync; `threads` = producers + consumers.  (An mbarrier would do as well, but
+// compute-sanitizer's racecheck does not see mbarrier waits as ordering ordinary st.shared / ld.shared pairs.)
+__device__ __forceinline__ void named_arrive(int id, int threads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void named_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // global -> shared bulk copy on the TMA engine, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
 {
@@ -441,10 +454,11 @@ __device__ __forceinline__ void make_schedule(const TcParams& p, Schedule& sch)
 // Epilogue of both GEMM kernels (warps 2-5): TMEM accumulator chunks of kNch columns -> per-set reductions -> global.
 // kScaleFromSmem: the row scales 20/max(|q|,1e-4) come from the converter warps of the same CTA (k_match_ts) instead of
 // the scale[] array k_pack_query wrote.
+constexpr int SCALE_FULL_BAR = 1, SCALE_FREE_BAR = 3;     // named barriers 1-2 and 3-4 (0 is __syncthreads)
+
 template <int kNch, bool kScaleFromSmem>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule& sch, uint32_t tmem_base, int warp, int lane,
-                                              uint64_t* s_tfull, uint64_t* s_tempty, uint64_t* s_scale_full,
-                                              const float (*s_scale)[BM])
+                                              uint64_t* s_tfull, uint64_t* s_tempty, const float (*s_scale)[BM])
 {
     const int nitems = p.ntiles * p.nsplit;
     const int lg = warp & 3;                       // TMEM lane group this warp may read
@@ -462,8 +476,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule&
         if (kScaleFromSmem) {
             sc = 0.f;
             if (c0 < sch.split_col[split + 1]) {     // the converters publish the row scales of every non-empty item
-                mbar_wait_relaxed(&s_scale_full[nz & 1], (nz >> 1) & 1);
+                named_sync(SCALE_FULL_BAR + (nz & 1), 256);              // 4 converter warps arrive, 4 epilogue warps wait
                 sc = s_scale[nz & 1][row_in_tile];
+                named_arrive(SCALE_FREE_BAR + (nz & 1), 256);            // the slot may be rewritten (item nz + 2)
                 ++nz;
             }
         } else {
@@ -620,7 +635,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
             }
         }
     } else {
-        epilogue_loop<NCH, false>(p, sch, tmem_base, warp, lane, s_tfull, s_tempty, nullptr, nullptr);
+        epilogue_loop<NCH, false>(p, sch, tmem_base, warp, lane, s_tfull, s_tempty, nullptr);
     }
 
     tc_fence_before();
@@ -652,7 +667,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
     constexpr int TS_B_BYTES = ts_b_bytes(TS_NCH), TS_STAGE_BYTES = ts_stage_bytes(TS_NCH);
     static_assert(TS_NCH % 16 == 0 && TS_A_SLOTS >= 2 && TS_STAGE_BYTES % 1024 == 0, "stage / TMEM layout");
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2], s_scale_full[2];
+    __shared__ uint64_t s_full[STAGES], s_empty[STAGES], s_tfull[2], s_tempty[2];
     __shared__ uint64_t s_afull[TS_A_SLOTS], s_aempty[TS_A_SLOTS];
     __shared__ float s_scale[2][BM];
     __shared__ uint32_t s_tmem;
@@ -668,7 +683,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_tfull[i], 1);
             mbar_init(&s_tempty[i], 4);
-            mbar_init(&s_scale_full[i], TS_CONV_WARPS);
         }
         for (int i = 0; i < TS_A_SLOTS; ++i) { mbar_init(&s_afull[i], TS_CONV_WARPS); mbar_init(&s_aempty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -744,7 +758,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
             }
         }
     } else if (warp < 6) {
-        epilogue_loop<TS_NCH, true>(p, sch, tmem_base, warp, lane, s_tfull, s_tempty, s_scale_full, s_scale);
+        epilogue_loop<TS_NCH, true>(p, sch, tmem_base, warp, lane, s_tfull, s_tempty, s_scale);
     } else {
         // ===== converters: raw fp32 row (shared memory) -> bf16 hi/lo -> TMEM operand slot =====
         const int lg = warp & 3, row = lg * 32 + lane;               // a warp may only touch its own TMEM lane quarter
@@ -795,9 +809,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
                 if (lane == 0) mbar_arrive(&s_afull[t]);
             };
             for (int kb = 0; kb < p.KB; ++kb) convert(std::true_type{});
+            if (nz >= 2) named_sync(SCALE_FREE_BAR + (nz & 1), 256);    // the epilogue has read item nz - 2's scales
             s_scale[nz & 1][row] = valid ? 20.0f / fmaxf(sqrtf(ssq), 1e-4f) : 0.f;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_scale_full[nz & 1]);
+            named_arrive(SCALE_FULL_BAR + (nz & 1), 256);
             ++nz;
             for (int rest = (nchunks - 1) * p.KB; rest > 0; --rest) convert(std::false_type{});
         }
