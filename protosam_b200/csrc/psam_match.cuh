@@ -29,6 +29,8 @@ bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want
 // the fused variant additionally needs dense slices (one 2-D tensor map over all query rows)
 bool match_ts_supported(const MatchParams& p);
 int match_reserve_sms(int n);
+// auto (algo 0): fused for narrow prototype tables, packed operands for wide ones (see the definition)
+bool match_ts_preferred(const MatchParams& p);
 size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fused);
 int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_bytes, bool fused, cudaStream_t stream);
 

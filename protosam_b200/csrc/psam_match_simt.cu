@@ -234,7 +234,8 @@ extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t ro
     // auto: tensor cores whenever the variant applies (the raw-similarity dump for visualisation and channel
     // counts that are not a multiple of 8 stay on the CUDA-core kernel) and the caller sized the workspace for it
     if (algo == 0 && match_tc_supported(Q, HW, C, nsets, cap_rows, sims != nullptr) && workspace) {
-        if (PSAM_AUTO_FUSED && match_ts_supported(p) && workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, true))
+        if (PSAM_AUTO_FUSED && match_ts_supported(p) && match_ts_preferred(p) &&
+            workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, true))
             return launch_match_tc(p, workspace, workspace_bytes, true, stream);
         if (workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, false))
             return launch_match_tc(p, workspace, workspace_bytes, false, stream);

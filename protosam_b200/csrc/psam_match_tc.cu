@@ -451,6 +451,22 @@ __device__ __forceinline__ void make_schedule(const TcParams& p, Schedule& sch)
     sch.split_col[p.nsplit] = T;
 }
 
+// The columns [c0, c1) of a work item are processed in accumulator-sized chunks.  Equal widths (in units of 16 columns)
+// instead of "full chunks + a remainder": the MMA's cost per column rises as N shrinks, and a 60-column tail chunk after
+// ten full ones (config 3: 2300 columns) costs a whole pass over the query tile for a quarter of the work.
+struct Chunks {
+    int n, base, rem;       // n chunks; chunk j is 16 * (base + (j < rem)) columns wide
+};
+
+__device__ __forceinline__ Chunks make_chunks(int cols, int nch_max)
+{
+    const int n = (cols + nch_max - 1) / nch_max, units = cols / 16;
+    return n > 0 ? Chunks{n, units / n, units % n} : Chunks{0, 0, 0};
+}
+
+__device__ __forceinline__ int chunk_start(const Chunks& c, int j) { return 16 * (j * c.base + min(j, c.rem)); }
+__device__ __forceinline__ int chunk_width(const Chunks& c, int j) { return 16 * (c.base + (j < c.rem ? 1 : 0)); }
+
 // Epilogue of both GEMM kernels (warps 2-5): TMEM accumulator chunks of kNch columns -> per-set reductions -> global.
 // kScaleFromSmem: the row scales 20/max(|q|,1e-4) come from the converter warps of the same CTA (k_match_ts) instead of
 // the scale[] array k_pack_query wrote.
@@ -485,8 +501,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule&
             sc = valid ? __ldg(p.scale + g) : 0.f;
         }
         const float sc2 = sc * LOG2E;
+        const Chunks ck = make_chunks(sch.split_col[split + 1] - c0, kNch);
         int col = 0;                                // column cursor relative to c0
-        int cur_chunk = -1;
+        int cur_chunk = -1, chunk_begin = 0, chunk_end = 0;
         uint32_t b = 0;
         for (int set = sch.split_set[split]; set < sch.split_set[split + 1]; ++set) {
             const int cnt = sch.count[set];
@@ -502,21 +519,22 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const Schedule&
             RowAcc a{0.f, 0.f, -CUDART_INF_F, 0};
             const bool is_mask = p.eff_modes[set] == PSAM_MODE_MASK;
             for (int nb = 0; nb < cnt; nb += 16, col += 16) {
-                const int chunk = col / kNch;
-                if (chunk != cur_chunk) {
+                if (col >= chunk_end) {             // next accumulator chunk (16-column groups never straddle chunks)
                     if (cur_chunk >= 0) {           // done with the previous accumulator buffer
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&s_tempty[b]);
                         ++cit;
                     }
+                    ++cur_chunk;
+                    chunk_begin = chunk_end;
+                    chunk_end += chunk_width(ck, cur_chunk);
                     b = cit & 1;
                     mbar_wait_relaxed(&s_tfull[b], (cit >> 1) & 1);
                     tc_fence_after();
-                    cur_chunk = chunk;
                 }
                 float v[16];
-                tc_ld16(lane_addr + b * kNch + (col - chunk * kNch), v);
+                tc_ld16(lane_addr + b * kNch + (col - chunk_begin), v);
                 const int nvalid = cnt - nb;
                 // the engine path asks for no `assign`: grid sets then need no maximum at all, 'mask' sets no exponential
                 if (is_mask) fold16_any<false, true, false>(v, nvalid, nb, sc2, a);
@@ -588,8 +606,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
                 const int tile = it / p.nsplit, split = it - tile * p.nsplit;
                 const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
                 const uint8_t* a_tile = p.a_img + (size_t)tile * p.KB * A_STAGE_BYTES;
-                for (int n0 = c0; n0 < c1; n0 += NCH) {
-                    const uint32_t bytes_b = (uint32_t)min(NCH, c1 - n0) * (GROUP_BYTES / 8);
+                const Chunks ck = make_chunks(c1 - c0, NCH);
+                for (int j = 0; j < ck.n; ++j) {
+                    const int n0 = c0 + chunk_start(ck, j);
+                    const uint32_t bytes_b = (uint32_t)chunk_width(ck, j) * (GROUP_BYTES / 8);
                     for (int kb = 0; kb < p.KB; ++kb, ++kit) {
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                         mbar_wait_relaxed(&s_empty[s], ph ^ 1);
@@ -609,12 +629,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_match_tc(const TcParams p)
             for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
                 const int split = it % p.nsplit;
                 const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
-                for (int n0 = c0; n0 < c1; n0 += NCH, ++cit) {
+                const Chunks ck = make_chunks(c1 - c0, NCH);
+                for (int j = 0; j < ck.n; ++j, ++cit) {
                     const uint32_t b = cit & 1, tph = (cit >> 1) & 1;
                     mbar_wait(&s_tempty[b], tph ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + b * NCH;
-                    const uint32_t idesc = make_idesc(min(NCH, c1 - n0));
+                    const uint32_t idesc = make_idesc(chunk_width(ck, j));
                     for (int kb = 0; kb < p.KB; ++kb, ++kit) {
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                         mbar_wait(&s_full[s], ph);
@@ -708,8 +729,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
             for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
                 const int tile = it / p.nsplit, split = it - tile * p.nsplit;
                 const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
-                for (int n0 = c0; n0 < c1; n0 += TS_NCH) {
-                    const uint32_t bytes_b = (uint32_t)min(TS_NCH, c1 - n0) * (GROUP_BYTES / 8);
+                const Chunks ck = make_chunks(c1 - c0, TS_NCH);
+                for (int j = 0; j < ck.n; ++j) {
+                    const int n0 = c0 + chunk_start(ck, j);
+                    const uint32_t bytes_b = (uint32_t)chunk_width(ck, j) * (GROUP_BYTES / 8);
                     for (int kb = 0; kb < p.KB; ++kb, ++kit) {
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                         mbar_wait_relaxed(&s_empty[s], ph ^ 1);
@@ -728,12 +751,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
             for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
                 const int split = it % p.nsplit;
                 const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
-                for (int n0 = c0; n0 < c1; n0 += TS_NCH, ++cit) {
+                const Chunks ck = make_chunks(c1 - c0, TS_NCH);
+                for (int j = 0; j < ck.n; ++j, ++cit) {
                     const uint32_t b = cit & 1, tph = (cit >> 1) & 1;
                     mbar_wait(&s_tempty[b], tph ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + b * TS_NCH;
-                    const uint32_t idesc = make_idesc(min(TS_NCH, c1 - n0));
+                    const uint32_t idesc = make_idesc(chunk_width(ck, j));
                     for (int kb = 0; kb < p.KB; ++kb, ++kit) {
                         const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                         const uint32_t t = kit % TS_A_SLOTS, aph = (kit / TS_A_SLOTS) & 1;
@@ -769,7 +793,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_match_ts(const TcParams p, co
             const int c0 = sch.split_col[split], c1 = sch.split_col[split + 1];
             if (c0 >= c1) continue;
             const bool valid = tile * BM + row < p.R;
-            const int nchunks = (c1 - c0 + TS_NCH - 1) / TS_NCH;
+            const int nchunks = make_chunks(c1 - c0, TS_NCH).n;
             float ssq = 0.f;
             // one k-block: this thread's row of the box -> 16 hi + 16 lo packed columns in TMEM operand slot t
             auto convert = [&](auto first_chunk) {
@@ -882,6 +906,23 @@ bool match_tc_supported(int Q, int HW, int C, int nsets, int cap_rows, bool want
 bool match_ts_supported(const MatchParams& p)
 {
     return p.Q == 1 || p.slice_stride == (int64_t)p.HW * p.row_stride;
+}
+
+// Which tensor-core variant algo 0 takes.  The fused kernel converts the query tile once per column chunk of the work item,
+// the packed-operand path once per launch (k_pack_query): with many chunks per item the conversions, the narrower
+// accumulators (224 instead of 256 columns) and the fused kernel's larger footprint beside the prompt kernels outweigh the
+// saved pass.  Measured on one B200 (ms per volume, fused / packed): config 2 (1.3 k columns, 2 x 3 chunks) 0.31 / 0.35,
+// config 5 (0.6 k, 3 chunks) 7.7 / 10.1, config 4 (1.3 k, 6 chunks) 2.01 / 2.13, config 3 (2.3 k, 11 chunks) 3.57 / 3.22.
+// The live column count is device-side data; the host only knows the table's capacity, of which the grid sets typically
+// fill about half (background sets most of their windows, foreground sets few): capacity >= 4096 columns -> packed.
+bool match_ts_preferred(const MatchParams& p)
+{
+    static int thresh = 0;
+    if (thresh == 0) {
+        thresh = 4096;
+        if (const char* ov = getenv("PSAM_TS_MAX_COLUMNS")) thresh = std::max(1, atoi(ov));
+    }
+    return (long long)p.nsets * tc::pad16(p.cap_rows) < thresh;
 }
 
 size_t match_tc_workspace(int Q, int HW, int C, int nsets, int cap_rows, bool fused)
