@@ -147,7 +147,11 @@ int psam_alp_proto_grid(const float* pooled, int S, int gh, int gw, int vw, floa
  *   sims       [Q,nsets,cap_rows,HW] or NULL: raw d ('raw_local_sims', vis_sim=True).
  *   status     [nsets] int32, PSAM_SET_EMPTY is OR-ed in for empty grid sets.
  *   algo       0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 split-bf16 tensor-core kernel fed from packed
- *              operand images, 3 = the same GEMM with the fp32 -> bf16 hi/lo conversion of the query fused into it.
+ *              operand images (a pack kernel writes the query's bf16 hi/lo image first), 3 = the fused tensor-core
+ *              kernel: the fp32 query is read through a 2-D tensor map, split into bf16 hi/lo inside the GEMM and used
+ *              as the A operand from TMEM (needs dense slices: slice_stride == HW * row_stride, or Q == 1).
+ *              auto = 3 for dense slices and tables of < 4096 columns capacity (nsets * pad16(cap_rows)), 2 for wider
+ *              tables / strided slices, 1 when sims != NULL, C % 8 != 0 or the workspace is too small.
  * ------------------------------------------------------------------------------------ */
 size_t psam_alp_match_workspace(int Q, int HW, int C, int nsets, int cap_rows, int algo);
 

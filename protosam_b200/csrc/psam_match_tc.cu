@@ -75,8 +75,8 @@ constexpr uint64_t UMMA_LAYOUT = BK == 64 ? 2 : 4;   // cute::UMMA::LayoutType S
 
 // physical 16-byte chunk of logical chunk c in row r of an 8-row atom (Swizzle<3,4,3> / Swizzle<2,4,3>)
 __host__ __device__ __forceinline__ int swz(int r, int c) { return BK == 64 ? (c ^ r) : (c ^ ((r >> 1) & 3)); }
-constexpr int A_STAGE_BYTES = BM / 8 * GROUP_BYTES;    // 32 KB
-constexpr int B_STAGE_BYTES = NCH / 8 * GROUP_BYTES;   // 64 KB
+constexpr int A_STAGE_BYTES = BM / 8 * GROUP_BYTES;    // 16 KB (BK = 32)
+constexpr int B_STAGE_BYTES = NCH / 8 * GROUP_BYTES;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 __host__ __device__ constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024; }  // + slack for the 1024-byte alignment
 constexpr int MAX_SETS = 128;

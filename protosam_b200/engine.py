@@ -166,10 +166,25 @@ class CoarseVolumeEngine:
             return dist.get_world_size(self.group), dist.get_rank(self.group)
         return 1, 0
 
-    def _channel(self, kind: str, payload_bytes: int, device) -> "ops.PeerChannel":
+    def _channel(self, kind: str, payload_bytes: int, device) -> Optional["ops.PeerChannel"]:
+        """The peer channel of this engine for `kind`, created on first use (collective).  If symmetric memory cannot be
+        set up on ANY rank (driver / container without peer mapping), every rank falls back to the NCCL path: the
+        ranks agree through one all-reduce, so nobody is left waiting in a one-sided protocol."""
         ch = self._channels.get(kind)
         if ch is None or ch.payload_bytes < payload_bytes:
-            ch = ops.PeerChannel(payload_bytes, self.group, device)
+            err = None
+            try:
+                ch = ops.PeerChannel(payload_bytes, self.group, device)
+            except Exception as e:      # noqa: BLE001 -- whatever the allocator / rendezvous raises
+                ch, err = None, e
+            ok = torch.tensor([0 if ch is None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                import warnings
+                warnings.warn(f"protosam_b200: peer-memory exchanges unavailable ({err!r}); using NCCL collectives")
+                self.p2p = False
+                self._channels.clear()
+                return None
             self._channels[kind] = ch
         return ch
 
@@ -182,6 +197,8 @@ class CoarseVolumeEngine:
         if not self.p2p:
             return broadcast_prototypes(protos, src=src, group=self.group)
         ch = self._channel("table", protos["packed"].numel(), protos["packed"].device)
+        if ch is None:
+            return broadcast_prototypes(protos, src=src, group=self.group)
         if rank == src:
             ops.peer_push_table(ch, protos)
         else:
@@ -196,6 +213,8 @@ class CoarseVolumeEngine:
         world, rank = self._world()
         slot = (buf.numel() + 15) // 16 * 16
         ch = self._channel("records", slot * world, buf.device)
+        if ch is None:
+            return gather_packed(buf, counts, layout, dst=dst, group=self.group, async_op=async_op)
         assert ch.payload_bytes // world // 16 * 16 == slot, "collect_records: the record buffer size changed"
         ops.peer_put(ch, buf, dst)
         bucket = None
@@ -363,6 +382,7 @@ class GraphedVolumeStep:
         _, _, buf0 = eng.prompts_from_logits(eng.match(qry_local), n_alloc=n_alloc, return_packed=True)
         if p2p:
             eng.collect_records(buf0, self.counts, self.layout, dst=dst)
+            p2p = bool(eng.p2p)          # the engine falls back to NCCL when peer channels cannot be created
         torch.cuda.current_stream().synchronize()
         self.g1 = None
         k0 = ops._lib.launch_count()
