@@ -63,6 +63,30 @@ def test_argument_errors_are_reported_not_crashed(lib):
     assert rc == -1 and b"null pointer" in lib.psam_last_error()
 
 
+def test_new_entry_points_check_their_arguments(lib):
+    """psam_topk_points, psam_peer_*, psam_match_reserve_sms: argument errors come back as codes + messages (no GPU needed:
+    the checks run before anything is enqueued)"""
+    one = ctypes.c_void_p(16)                      # a non-null, 16-byte aligned dummy pointer: never dereferenced
+    rc = lib.psam_topk_points(one, one, 0, one, one, 1, 64, 4, 0, 65, one, one, one, 1 << 30, None)
+    assert rc == -1 and b"k = 65" in lib.psam_last_error()
+    rc = lib.psam_topk_points(one, one, 0, one, one, 1, 64, 4, 0, 3, one, one, None, 0, None)
+    assert rc == -2 and b"workspace" in lib.psam_last_error()
+    assert lib.psam_topk_points_workspace(2, 8, 3) >= 2 * 8 * 64 * 3 * 8
+    assert lib.psam_peer_region_bytes(1000) == 4096 + 1024
+    rc = lib.psam_peer_put(one, 32, 32, one, 1, 0, 0, one, None)             # world < 2
+    assert rc == -1 and b"world" in lib.psam_last_error()
+    rc = lib.psam_peer_put(one, 24, 32, one, 2, 0, 1, one, None)             # not a multiple of 16 bytes
+    assert rc == -1
+    rc = lib.psam_peer_push_table(one, 8, 10, 6, 0, 0, one, 2, 0, one, None)   # C % 4, integer arrays inside the rows
+    assert rc == -1 and b"geometry" in lib.psam_last_error()
+    rc = lib.psam_peer_recv_table(one, 8, 10, 8, 8 * 10 * 8 * 4, 96, one, 2, 1, 1, one, None)   # src == rank
+    assert rc == -1
+    prev = lib.psam_match_reserve_sms(5)
+    assert lib.psam_match_reserve_sms(-1) == 5
+    lib.psam_match_reserve_sms(prev)
+    assert lib.psam_match_reserve_sms(-1) == prev
+
+
 def test_product_never_imports_the_oracle():
     """the oracle is test infrastructure: nothing under protosam_b200/ may reference it"""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "protosam_b200")):
