@@ -299,7 +299,7 @@ int psam_coarse_to_prompts(const float* logits, int n_img, int h, int w, int mid
  * 16 zero-initialised bytes of local device memory: one for a table channel (push and recv share it), two for a record
  * channel (put, collect); epochs live there, so the calls can be captured into CUDA graphs.  Source and destination
  * ranks may change from one exchange to the next.  Every rank must issue the matching calls in the same order; a peer that never answers
- * traps the waiting kernel after 20 s instead of hanging the GPU.
+ * traps the waiting kernel after 120 s instead of hanging the GPU.
  *
  *   psam_peer_push_table  (source rank) waits until every peer acknowledged the previous table, writes the LIVE rows
  *                         (counts[s] of cap_rows per set) + the integer arrays of its prototype table into every peer's

@@ -21,7 +21,7 @@ namespace psam {
 
 constexpr int PEER_THREADS = 256;
 constexpr int PEER_MAX_WORLD = 64;
-constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;     // a lost peer traps instead of hanging the GPU
+constexpr unsigned long long PEER_TIMEOUT_NS = 120ull * 1000 * 1000 * 1000;    // a lost peer traps instead of hanging the GPU
 
 // signal words (uint32) of a region: READY[r] raised by writer rank r, ACK[r] raised by reader rank r
 __device__ __forceinline__ uint32_t* sig_ready(void* region, int r) { return reinterpret_cast<uint32_t*>(region) + r; }
