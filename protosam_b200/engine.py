@@ -159,6 +159,7 @@ class CoarseVolumeEngine:
         # (a collective, blocking step: the first set_support / run_sharded must not be inside a graph capture)
         self.p2p = bool(p2p)
         self._channels = {}
+        self._retired = []
 
     # -- distributed helpers -------------------------------------------------------------------
     def _world(self):
@@ -183,8 +184,9 @@ class CoarseVolumeEngine:
                 import warnings
                 warnings.warn(f"protosam_b200: peer-memory exchanges unavailable ({err!r}); using NCCL collectives")
                 self.p2p = False
-                self._channels.clear()
                 return None
+            if kind in self._channels:
+                self._retired.append(self._channels[kind])       # CUDA graphs captured earlier still point into it
             self._channels[kind] = ch
         return ch
 
@@ -215,7 +217,7 @@ class CoarseVolumeEngine:
         ch = self._channel("records", slot * world, buf.device)
         if ch is None:
             return gather_packed(buf, counts, layout, dst=dst, group=self.group, async_op=async_op)
-        assert ch.payload_bytes // world // 16 * 16 == slot, "collect_records: the record buffer size changed"
+        slot = ch.payload_bytes // world // 16 * 16          # the channel's slot size (>= this buffer)
         ops.peer_put(ch, buf, dst)
         bucket = None
         if rank == dst:
