@@ -685,10 +685,10 @@ def gpu_arm(args, cfg):
                        "converted inside the GEMM, A operand in TMEM"),
         "k_match_tc": ("tensor", flops_match, "2*HW*C*sum(P) per slice; executed = 3x (split-bf16 passes)"),
         "k_match_simt": ("tensor", flops_match, "2*HW*C*sum(P) per slice on CUDA cores"),
-        "k_blocks_warp": ("hbm", n_img * (8.0 * h * w + out * out / 8.0) + 4.0 * n_fg,
-                          "per image: 8*h*w logits + out^2/8 mask bits + 4*n_fg probabilities (upper bound: p_fg is written "
-                          "only where kernel 3b reads it).  The kernel is CUDA-core ISSUE-bound, not HBM-bound: see "
-                          "issue_slot_busy_pct (ncu) beside the byte fraction"),
+        "k_blocks_warp": ("issue", n_img * (8.0 * h * w + out * out / 8.0) + 4.0 * n_fg,
+                          "CUDA-core ISSUE-bound (exact ATen-CPU arithmetic per pixel): achieved = issue slots busy, from the "
+                          "ncu capture in profiles/ (smsp__issue_active); algorithmic bytes per image for reference: 8*h*w "
+                          "logits + out^2/8 mask bits + 4*n_fg probabilities"),
         "k_components": ("hbm", n_img * (out * out / 8.0 + 64.0) + 4.0 * n_fg + 96.0 * n_cc,
                          "per image: out^2/8 mask bits + 4*n_fg probabilities + 96 B per component (latency-bound integer work)"),
         "k_pack_query": ("hbm", 8.0 * q_local * h * w * C, "4*C*HW read + 4*C*HW operand image written per slice"),
@@ -700,6 +700,8 @@ def gpu_arm(args, cfg):
     sec = ms_dom / n_dom * 1e-3
     if bound == "tensor":
         ach, peak, unit = work / sec / 1e12, peak_tf, "TFLOP/s"
+    elif bound == "issue":
+        ach, peak, unit = float(traffic_tab.get("issue_slot_busy_pct", {}).get(dom, 0.0)), 100.0, "% of issue slots (ncu)"
     else:
         ach, peak, unit = work / sec / 1e9, peak_bw, "GB/s"
     roof = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
