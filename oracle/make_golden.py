@@ -382,6 +382,40 @@ def gen_variants():
     print("variants:", len(names), "cases")
 
 
+def gen_topk():
+    """ProtoSAM.get_most_conf_points(output_p_fg, pred, k) for k > 1 (models/ProtoSAM.py:266-289), called as the
+    reference defines it, on the 1024^2 probability maps of the prompt cases: per case and k, the first components (cv2
+    label order) that have at least k pixels."""
+    _, PS, uu = ref_shims.load_pipeline()
+    store = {"versions": _versions()}
+    names = []
+    for name, low, S in variant_cases():
+        logits_S = F.interpolate(torch.from_numpy(low), size=(S, S), mode="bilinear")
+        lg = F.interpolate(logits_S, size=(1024, 1024), mode="bilinear")
+        P = lg.softmax(1)
+        pred = np.array(P.argmax(1)[0])
+        cc, _ = uu.get_connected_components(pred, lg)
+        if cc[0] <= 1:
+            continue
+        names.append(name)
+        store[f"{name}/low"] = low
+        store[f"{name}/S"] = np.array(S)
+        for k in (2, 5, 17):
+            labs, locs, confs = [], [], []
+            for j in range(1, cc[0]):
+                if cc[2][j, 4] < k or len(labs) >= 6:
+                    continue
+                loc, conf = PS.ProtoSAM.get_most_conf_points(None, P[0, 1], torch.from_numpy(cc[1] == j), k)
+                labs.append(j); locs.append(loc); confs.append(np.array(conf, np.float64))
+            store[f"{name}/k{k}/labels"] = np.array(labs, np.int64)
+            if labs:
+                store[f"{name}/k{k}/locations"] = np.stack(locs)
+                store[f"{name}/k{k}/confidences"] = np.stack(confs)
+    store["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "topk.npz"), **store)
+    print("topk:", len(names), "cases")
+
+
 def main():
     assert ref_shims.reference_available(), "reference tree not mounted"
     os.makedirs(GOLD, exist_ok=True)
@@ -391,6 +425,7 @@ def main():
     gen_alp_config_shapes2()
     gen_prompts()
     gen_variants()
+    gen_topk()
 
 
 if __name__ == "__main__":

@@ -421,6 +421,25 @@ def dilate_square(mask, iterations=10):
     return out
 
 
+def get_most_conf_points(p_fg, pred, k):
+    """ProtoSAM.get_most_conf_points (models/ProtoSAM.py:266-289) for any k: (locations int64 [k,2] in (x, y),
+    [confidences]) = torch.nonzero(mask)[torch.topk(p_fg[mask], k).indices], torch.topk's order among equal values
+    replayed (psamo_topk_pos); (None, None) for an empty mask."""
+    L = lib()
+    mask = np.asarray(pred).astype(bool)
+    ys, xs = np.nonzero(mask)
+    if len(ys) == 0:
+        return None, None
+    v = _f32(np.asarray(p_fg)[ys, xs])
+    if k > len(v):
+        raise RuntimeError("selected index k out of range")
+    pos = np.zeros(k, np.int32)
+    L.psamo_topk_pos.restype = ctypes.c_int
+    rc = L.psamo_topk_pos(_ptr(v), int(len(v)), int(k), pos.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return np.stack([xs[pos], ys[pos]], 1).astype(np.int64), [float(c) for c in v[pos]]
+
+
 def _topk1_masked(values, mask):
     """get_most_conf_points(values, mask, 1) (models/ProtoSAM.py:266-289): (x, y) of torch.topk(values[mask], 1), or
     None when the mask is empty."""

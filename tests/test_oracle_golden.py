@@ -223,3 +223,25 @@ def test_protomedsam_boxes(name, use_cca):
         want = g[f"{name}/medsam_conf"]
         got = np.array([float(out["conf"][k]) for k in sorted(out["conf"])])
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
+
+
+def _topk_names():
+    return list(_load("topk.npz")["names"])
+
+
+@pytest.mark.parametrize("name", _topk_names())
+@pytest.mark.parametrize("k", [2, 5, 17])
+def test_most_conf_points_any_k(name, k):
+    """ProtoSAM.get_most_conf_points(output_p_fg, pred, k) for k > 1 (models/ProtoSAM.py:266-289), as the reference computes
+    it on the 1024^2 probability map: locations in torch.topk's order (equal probabilities included) and the confidences."""
+    g = _load("topk.npz")
+    labels = g[f"{name}/k{k}/labels"]
+    if len(labels) == 0:
+        pytest.skip("no component with k pixels")
+    out, p, cc = _variant_setup(g, name, False)
+    for i, j in enumerate(labels):
+        loc, conf = O.get_most_conf_points(p[0, 1], cc[1] == j, k)
+        assert loc.dtype == np.int64 and np.array_equal(loc, g[f"{name}/k{k}/locations"][i]), (name, k, int(j))
+        assert np.array_equal(np.array(conf, np.float64), g[f"{name}/k{k}/confidences"][i])
+    with pytest.raises(RuntimeError):
+        O.get_most_conf_points(p[0, 1], cc[1] == labels[0], int((cc[1] == labels[0]).sum()) + 1)
