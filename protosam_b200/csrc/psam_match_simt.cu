@@ -235,8 +235,10 @@ extern "C" int psam_alp_match(const float* qry, int64_t slice_stride, int64_t ro
     // counts that are not a multiple of 8 stay on the CUDA-core kernel) and the caller sized the workspace for it
     if (algo == 0 && match_tc_supported(Q, HW, C, nsets, cap_rows, sims != nullptr) && workspace) {
         if (PSAM_AUTO_FUSED && match_ts_supported(p) && match_ts_preferred(p) &&
-            workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, true))
-            return launch_match_tc(p, workspace, workspace_bytes, true, stream);
+            workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, true)) {
+            const int rc = launch_match_tc(p, workspace, workspace_bytes, true, stream);
+            if (rc != PSAM_ERR_UNSUPPORTED) return rc;          // no tensor map for this shape / driver: nothing was enqueued
+        }
         if (workspace_bytes >= match_tc_workspace(Q, HW, C, nsets, cap_rows, false))
             return launch_match_tc(p, workspace, workspace_bytes, false, stream);
     }

@@ -1030,6 +1030,12 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     uint8_t* b_img = base;
     uint8_t* a_img = fused ? nullptr : b_img + align_up(L.b_bytes, 1024);
     float* scale = fused ? nullptr : reinterpret_cast<float*>(a_img + align_up(L.a_bytes, 1024));
+    // the tensor map of the fused kernel is host work: built before anything is enqueued, so that a failure (driver
+    // without cuTensorMapEncodeTiled, a shape the encoder rejects) leaves no trace and auto can take the packed path
+    CUtensorMap qmap;
+    if (fused) {
+        if (int rc = make_query_map(p, L.R, &qmap)) return rc == PSAM_ERR_LAUNCH ? PSAM_ERR_UNSUPPORTED : rc;
+    }
 
     PSAM_PROF_BEGIN(stream);
     PSAM_MAX_CARVEOUT(k_pack_protos);
@@ -1065,8 +1071,6 @@ int launch_match_tc(const MatchParams& p, void* workspace, size_t workspace_byte
     const bool three = MAX_STAGES >= 4 && gemm_stages() == 3;
     static bool set_tc3[64] = {}, set_tc4[64] = {};
     if (fused) {
-        CUtensorMap qmap;
-        if (int rc = make_query_map(p, L.R, &qmap)) return rc;
         // 4 stages of 44 KB by default: unlike the packed kernel, a stage's cycle includes the conversion, and the fourth
         // stage is worth 12 % to the kernel and 4 % to the pipelined step (measured); PSAM_TS_STAGES / PSAM_TS_NCH are
         // experiment knobs
